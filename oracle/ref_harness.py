@@ -1,0 +1,110 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference Python.
+
+Puts ``/root/reference`` on ``sys.path`` with ``tensorflow`` / ``keras`` /
+``matplotlib`` stubbed in ``sys.modules`` (none are installed here, there is no
+network) so that ``Checkers.py``, ``MCTS.py`` and ``training_pipeline.py`` run
+verbatim.  Used (a) by ``tests/golden/make_golden.py`` to produce the committed
+golden vectors and (b) by the ``needs_reference`` CPU tests that pin the C
+oracle (``oracle/ck_oracle.c``) against the real reference where it is mounted.
+
+``/root/reference`` does not exist on the GPU box: nothing under ``-m gpu``,
+``smoke()`` or ``bench.py`` imports this module.
+"""
+import contextlib
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_DIR = os.environ.get("CK_REFERENCE_DIR", "/root/reference")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "Checkers.py"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_LOAD_MODEL_HOOK = {"fn": None}
+
+
+def set_load_model(fn):
+    """``fn(path) -> object with Keras-like .predict(x[B,8,8,14]) -> [p[B,512], v[B,1]]``."""
+    _LOAD_MODEL_HOOK["fn"] = fn
+
+
+def _load_model(path, *a, **k):
+    if _LOAD_MODEL_HOOK["fn"] is None:
+        raise RuntimeError("ref_harness.set_load_model() was not called")
+    return _LOAD_MODEL_HOOK["fn"](path)
+
+
+def install_stubs():
+    """Stub list from SURVEY.md appendix A (training_pipeline.py:31-40 imports)."""
+    if "tensorflow" in sys.modules and getattr(sys.modules["tensorflow"], "_ck_stub", False):
+        return
+
+    class Sequence(object):
+        pass
+
+    class Callback(object):
+        def __init__(self, *a, **k):
+            pass
+
+    tf = _stub("tensorflow", _ck_stub=True)
+    keras = _stub("tensorflow.keras")
+    tf.keras = keras
+    keras.utils = _stub("tensorflow.keras.utils", Sequence=Sequence)
+    keras.callbacks = _stub("tensorflow.keras.callbacks", Callback=Callback)
+    keras.backend = _stub("tensorflow.keras.backend")
+    keras.models = _stub("tensorflow.keras.models", load_model=_load_model)
+    k2 = _stub("keras")
+    k2.callbacks = _stub("keras.callbacks", Callback=Callback)
+    k2.backend = _stub("keras.backend")
+    mpl = _stub("matplotlib")
+    mpl.pyplot = _stub("matplotlib.pyplot")
+
+
+_REF_MODULE_NAMES = ("Checkers", "MCTS", "training_pipeline", "TicTacToe",
+                     "CLR", "CLR.clr_callback", "LRFinder", "LRFinder.keras_callback")
+
+
+@contextlib.contextmanager
+def reference_modules(with_pipeline=False):
+    """Context manager yielding a namespace with the reference's own modules.
+
+    The repo ships drop-in modules with the same names (``Checkers``, ``MCTS``,
+    ``training_pipeline``); to keep the two apart the reference copies are
+    imported under a temporary ``sys.path``/``sys.modules`` and removed again on
+    exit, and the caller keeps the module objects.
+    """
+    if not reference_available():
+        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_DIR)
+    saved = {n: sys.modules.pop(n) for n in _REF_MODULE_NAMES if n in sys.modules}
+    saved_path = list(sys.path)
+    sys.path.insert(0, REFERENCE_DIR)
+    try:
+        ns = types.SimpleNamespace()
+        ns.Checkers = importlib.import_module("Checkers")
+        ns.MCTS = importlib.import_module("MCTS")
+        if with_pipeline:
+            install_stubs()
+            ns.training_pipeline = importlib.import_module("training_pipeline")
+        assert os.path.dirname(ns.Checkers.__file__) == REFERENCE_DIR
+        yield ns
+    finally:
+        sys.path[:] = saved_path
+        for n in _REF_MODULE_NAMES:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved)
+
+
+def load_reference(with_pipeline=False):
+    """Non-context variant: returns the namespace, leaves sys.modules clean."""
+    with reference_modules(with_pipeline) as ns:
+        return ns
