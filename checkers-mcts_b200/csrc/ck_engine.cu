@@ -1,0 +1,1159 @@
+// ck_engine.cu -- K2/K5/K6: batched PUCT self-play / arena engine, one warp per game.
+//
+// Replaces the reference's sequential Python loop
+//   generate_Checkers_data._generate_data (training_pipeline.py:334-419)
+//   tournament_Checkers._start_tournament (:505-559)
+//   MCTS.begin_tree_search / tree_policy / select_child / backpropagation / best_child /
+//   new_root_node (MCTS.py:59-295), MCTS_Node (:345-430)
+// with a lock-step device loop: every round runs ONE tree kernel (consume the previous
+// evaluation -> expand + backup -> play moves / re-root when a search is complete -> PUCT
+// descent to the next leaf -> stage its network input) and ONE batched evaluation of all
+// staged leaves.  Simulations that end in a terminal child need no evaluation and are
+// finished inside the tree kernel.
+//
+// HBM layout (per engine):
+//   pos [slot][3 buffers][cap]  uint4  p1,p2,k,meta                      16 B / node
+//   stat[slot][3 buffers][cap]  uint4  N (u32), W (f32), P (f32), link   16 B / node
+//     link = first_child[0:22) | n_children[22:28) | status[28:30) | parent_player[30]
+//   Each game owns two trees (one per colour, training_pipeline.py:353,372) living in two
+//   of its three buffers; the third is the to-space of the re-root compaction (K5).
+//   Children of a node are contiguous and stored in node.children order (legal list
+//   reversed, MCTS.py:72-75), so a PUCT step is one coalesced 16 B x b load.
+//   hist[slot][max_plies+1] ck_pos, path[slot][128] u32, leaves/policy/value per net.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "ck_common.cuh"
+#include "ck_device_fn.cuh"
+#include "ck_net.cuh"
+#include "ck_rules.cuh"
+
+namespace ck {
+
+constexpr int kMaxDepth = 128;
+constexpr int kWarpsPerBlock = 4;
+constexpr uint32_t kFcMask = 0x3FFFFFu;
+constexpr int kPowTable = 1 << 17;
+constexpr int kNoIdx = 1 << 30;
+
+enum { PH_NEED_ROOT = 0, PH_SEARCH = 1, PH_HALT = 2 };
+
+struct Slot {
+    int32_t game;            // local game index, -1 idle
+    int32_t hist_len, move_count, phase, cur, sims_done;
+    int32_t pend_leaf, pend_row, pend_depth, pend_net;
+    int32_t buf[2], scratch;
+    int32_t root[2], alloc[2], best[2], exists[2];
+    int32_t nrec, misses, search_id, manual, manual_target;
+    int32_t pad;
+    double tau;
+    unsigned long long tot_sims, tot_evals;      // monotonic per slot; per-game totals are deltas
+    unsigned long long g_sims0, g_evals0;
+};
+
+struct Counters {
+    unsigned long long games_finished, moves, nodes, compactions;
+    int32_t next_game, error, halted, active;
+    int32_t batch_count[2];
+};
+
+struct EngineDev {
+    ck_engine_cfg cfg;
+    int32_t n_slots, cap, max_plies, max_rec, n_games, compact_need, max_term, arena_half;
+    float one_minus_eps;
+    uint4 *pos, *stat;
+    ck_pos *hist;
+    uint32_t *path;
+    Slot *slots;
+    Counters *ctr;
+    ck_leaf *leaves[2];
+    float *policy[2], *value[2];
+    ck_record *rec;
+    ck_game_result *results;
+    const double *pow_half;      // host libm pow(n, 0.5) table (MCTS.py:110 uses n ** 0.5)
+};
+
+// ---- small device helpers --------------------------------------------------------------
+__device__ __forceinline__ ck_pos to_pos(const uint4 v) { ck_pos p; p.p1 = v.x; p.p2 = v.y; p.k = v.z; p.meta = v.w; return p; }
+__device__ __forceinline__ uint4 from_pos(const ck_pos &p) { return make_uint4(p.p1, p.p2, p.k, p.meta); }
+__device__ __forceinline__ int link_nchild(uint32_t l) { return (int)((l >> 22) & 63u); }
+__device__ __forceinline__ int link_status(uint32_t l) { return (int)((l >> 28) & 3u); }
+__device__ __forceinline__ int link_pp(uint32_t l) { return (int)((l >> 30) & 1u); }
+__device__ __forceinline__ bool same_state(const ck_pos &a, const ck_pos &b) {
+    return a.p1 == b.p1 && a.p2 == b.p2 && a.k == b.k && ((a.meta ^ b.meta) & 1u) == 0;
+}
+__device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
+    v.x = __shfl_sync(CK_FULL, v.x, src); v.y = __shfl_sync(CK_FULL, v.y, src);
+    v.z = __shfl_sync(CK_FULL, v.z, src); v.w = __shfl_sync(CK_FULL, v.w, src);
+    return v;
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(CK_FULL, lo, m); hi = __shfl_xor_sync(CK_FULL, hi, m);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(CK_FULL, lo, d); hi = __shfl_up_sync(CK_FULL, hi, d);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(CK_FULL, lo, src); hi = __shfl_sync(CK_FULL, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+struct WarpCtx {
+    const EngineDev &E;
+    Slot &S;                 // shared-memory copy of the slot
+    ck_pos *kids;            // shared, CK_MAX_CHILDREN entries
+    uint32_t *path;          // global, kMaxDepth entries
+    ck_pos *hist;            // global, max_plies + 1 entries
+    int slot, lane;
+    __device__ uint4 *pos_buf(int buf) const { return E.pos + ((int64_t)slot * 3 + buf) * E.cap; }
+    __device__ uint4 *stat_buf(int buf) const { return E.stat + ((int64_t)slot * 3 + buf) * E.cap; }
+    __device__ uint4 *pos_of(int t) const { return pos_buf(S.buf[t]); }
+    __device__ uint4 *stat_of(int t) const { return stat_buf(S.buf[t]); }
+};
+
+__device__ __forceinline__ int global_game(const EngineDev &E, int local) {
+    return E.cfg.game_id_base + local * (E.cfg.game_id_stride ? E.cfg.game_id_stride : 1);
+}
+__device__ __forceinline__ uint64_t game_key(const EngineDev &E, int local) {
+    return mix64(E.cfg.seed ^ mix64((uint64_t)(uint32_t)global_game(E, local) + 0x51ED270B1ull));
+}
+__device__ __forceinline__ int net_of(const EngineDev &E, int local_game, int player) {
+    if (!E.cfg.arena) return 0;
+    const int p1_net = global_game(E, local_game) < E.arena_half ? 0 : 1;   // training_pipeline.py:523-528
+    return player == 0 ? p1_net : 1 - p1_net;
+}
+
+__device__ void dev_error(const EngineDev &E, int code) { atomicCAS(&E.ctr->error, 0, code); }
+
+// MCTS_Node.backpropagation + MCTS.determine_reward (MCTS.py:148-186, 419-430): every node
+// on the path gets N += 1 and W += reward seen from the player to move in its PARENT.
+__device__ void backup(const WarpCtx &c, int depth, bool is_outcome, int outcome, float value, int leaf_player) {
+    uint4 *stat = c.stat_of(c.S.cur);
+    for (int d = c.lane; d <= depth; d += 32) {
+        const uint32_t x = c.path[d];
+        uint4 st = stat[x];
+        const int pp = link_pp(st.w);
+        float reward;
+        if (is_outcome) {
+            if (outcome == CK_P1_WINS) reward = pp == 0 ? 1.f : -1.f;
+            else if (outcome == CK_P2_WINS) reward = pp == 1 ? 1.f : -1.f;
+            else reward = 0.f;
+        } else {
+            reward = leaf_player != pp ? -value : value;
+        }
+        st.x += 1u;
+        st.y = __float_as_uint(__fadd_rn(__uint_as_float(st.y), reward));
+        *reinterpret_cast<uint2 *>(&stat[x]) = make_uint2(st.x, st.y);
+    }
+    __syncwarp();
+}
+
+// Marsaglia-Tsang gamma(alpha) from Philox words (np.random.dirichlet, MCTS.py:108);
+// statistical parity only (SURVEY 8b RNG row)
+__device__ double gamma_sample(const Philox &rng, uint32_t c0, uint32_t c1, uint32_t c2, double alpha) {
+    uint32_t r[4];
+    if (alpha == 1.0) { rng(c0, c1, c2, 0x44495231u, r); return -log(u01(r[0], r[1])); }
+    const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+    const double d = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+    double out = d;
+    for (uint32_t it = 0; it < 64; ++it) {
+        rng(c0, c1, c2, 0x47414D00u + it, r);
+        const double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        double v = 1.0 + cc * x;
+        if (v <= 0) continue;
+        v = v * v * v;
+        uint32_t q[4];
+        rng(c0, c1, c2, 0x47414E00u + it, q);
+        if (log(u01(q[0], q[1])) < 0.5 * x * x + d - d * v + d * log(v)) { out = d * v; break; }
+    }
+    if (alpha < 1.0) { rng(c0, c1, c2, 0x47414F00u, r); out *= pow(u01(r[0], r[1]), 1.0 / alpha); }
+    return out;
+}
+
+// PUCT score of one child (MCTS.select_child, MCTS.py:101-116) with the dtypes numpy >= 2
+// produces: q = f32(W/N), (1-eps)*P in f32, everything else left-to-right in f64.
+__device__ __forceinline__ double puct(const EngineDev &E, const uint4 cst, double noise, double sqrt_n) {
+    const uint32_t n = cst.x;
+    const float q = n ? __fdiv_rn(__uint_as_float(cst.y), (float)n) : 0.f;
+    const float scaled = __fmul_rn(E.one_minus_eps, __uint_as_float(cst.z));
+    const double psa = __dadd_rn((double)scaled, __dmul_rn(E.cfg.epsilon, noise));
+    const double t = __ddiv_rn(__dmul_rn(__dmul_rn(E.cfg.uct_c, psa), sqrt_n), (double)(1u + n));
+    return __dadd_rn((double)q, t);
+}
+
+// One descent from the root (MCTS.tree_policy, MCTS.py:59-99).  Returns the leaf to evaluate
+// (depth in *out_depth), -1 when the descent ended in a terminal child (already backed up),
+// -2 on error.
+__device__ int select_leaf(const WarpCtx &c, int *out_depth) {
+    const EngineDev &E = c.E;
+    const int t = c.S.cur;
+    const uint4 *stat = c.stat_of(t);
+    const Philox rng(game_key(E, c.S.game));
+    int node = c.S.root[t], depth = 0;
+    if (c.lane == 0) c.path[0] = (uint32_t)node;
+    uint4 st = stat[node];
+    for (;;) {
+        const int b = link_nchild(st.w);
+        if (b == 0) { *out_depth = depth; __syncwarp(); return node; }
+        const int fc = (int)(st.w & kFcMask);
+        const uint32_t pn = st.x;
+        const double sqrt_n = pn < (uint32_t)kPowTable ? E.pow_half[pn] : sqrt((double)pn);
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        if (c.lane < b) c0 = stat[fc + c.lane];
+        if (c.lane + 32 < b) c1 = stat[fc + 32 + c.lane];
+        double n0 = 0.0, n1 = 0.0;
+        if (E.cfg.epsilon != 0.0) {                      // fresh Dirichlet(alpha) at every node, every visit (:107-108)
+            const uint32_t cc0 = (uint32_t)c.S.search_id, cc1 = (uint32_t)c.S.sims_done;
+            const double g0 = c.lane < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | c.lane), E.cfg.alpha) : 0.0;
+            const double g1 = c.lane + 32 < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), E.cfg.alpha) : 0.0;
+            double tot = g0 + g1;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tot += shfl_xor_d(tot, o);
+            n0 = g0 / tot; n1 = g1 / tot;
+        }
+        double best_u = 0.0;
+        int best_i = kNoIdx;
+        if (c.lane < b) { best_u = puct(E, c0, n0, sqrt_n); best_i = c.lane; }
+        if (c.lane + 32 < b) {
+            const double u1 = puct(E, c1, n1, sqrt_n);
+            if (u1 > best_u) { best_u = u1; best_i = c.lane + 32; }    // np.argmax: first maximum wins
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ou = shfl_xor_d(best_u, o);
+            const int oi = __shfl_xor_sync(CK_FULL, best_i, o);
+            const bool take = (oi != kNoIdx) && (best_i == kNoIdx || ou > best_u || (ou == best_u && oi < best_i));
+            if (take) { best_u = ou; best_i = oi; }
+        }
+        const uint4 pick = best_i < 32 ? shfl4(c0, best_i) : shfl4(c1, best_i - 32);
+        node = fc + best_i;
+        ++depth;
+        if (depth >= kMaxDepth) { dev_error(E, CK_ERR_DEPTH); *out_depth = depth - 1; return -2; }
+        if (c.lane == 0) c.path[depth] = (uint32_t)node;
+        const int cs = link_status(pick.w);
+        if (cs != CK_ONGOING) {                         // terminal child: no evaluation (:93-94,145-146)
+            __syncwarp();
+            backup(c, depth, true, cs, 0.f, 0);
+            return -1;
+        }
+        st = pick;
+    }
+}
+
+// stage the network input of a leaf (Checkers.predict, Checkers.py:431-432)
+__device__ void stage_leaf(const WarpCtx &c, int leaf, int depth) {
+    const EngineDev &E = c.E;
+    Slot &S = c.S;
+    __syncwarp();
+    if (c.lane == 0) {
+        const int net = net_of(E, S.game, S.cur);
+        const ck_pos p = to_pos(c.pos_of(S.cur)[leaf]);
+        ck_leaf L;
+        int p5;
+        const int cnt = gen_moves(p, NullSink{}, L.mask);
+        outcome_of(p, cnt > 0, &p5);
+        L.p1 = p.p1; L.p2 = p.p2; L.k = p.k;
+        L.info = (p.meta & 1u) | ((uint32_t)p5 << 8) | (((uint32_t)global_game(E, S.game) & 0xFFFFu) << 16);
+        const int row = atomicAdd(&E.ctr->batch_count[net], 1);
+        E.leaves[net][row] = L;
+        S.pend_leaf = leaf; S.pend_row = row; S.pend_depth = depth; S.pend_net = net;
+    }
+    __syncwarp();
+}
+
+// Expansion of the evaluated leaf (MCTS.py:71-77): all children at once in reversed legal
+// order, each with its own terminal test (MCTS_Node.__init__, :374-375), priors from the
+// masked + renormalised policy (Checkers.py:434-452), then the signed value backup.
+__device__ void expand_pending(const WarpCtx &c) {
+    const EngineDev &E = c.E;
+    Slot &S = c.S;
+    const int t = S.cur, leaf = S.pend_leaf, net = S.pend_net;
+    uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
+    const ck_pos lp = to_pos(pos[leaf]);
+    uint32_t mask[8];
+    int b = 0;
+    if (c.lane == 0) b = gen_moves(lp, ArraySink{c.kids, CK_MAX_CHILDREN}, mask);
+    b = __shfl_sync(CK_FULL, b, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mask[i] = __shfl_sync(CK_FULL, mask[i], 0);
+    __syncwarp();
+    const float *prow = E.policy[net] + (int64_t)S.pend_row * CK_POLICY_SIZE;
+    float masked[16];
+    const float psum = masked_policy_sum(prow, mask, c.lane, masked);
+    const float value = E.value[net][S.pend_row];
+    const int fc = S.alloc[t];
+    if (fc + b > E.cap) {
+        dev_error(E, CK_ERR_POOL_OVERFLOW);
+        if (c.lane == 0) { S.pend_leaf = -1; S.phase = PH_HALT; }
+        __syncwarp();
+        return;
+    }
+    const int lplayer = meta_player(lp.meta);
+    for (int i = c.lane; i < b; i += 32) {
+        const ck_pos ch = c.kids[b - 1 - i];            // node.children = legal list reversed (:72-75)
+        int p5;
+        const int stc = status_of(ch, &p5);
+        const float prior = __fdiv_rn(prow[meta_action(ch.meta)], psum);
+        pos[fc + i] = from_pos(ch);
+        stat[fc + i] = make_uint4(0u, __float_as_uint(0.f), __float_as_uint(prior),
+                                  ((uint32_t)stc << 28) | ((uint32_t)lplayer << 30));
+    }
+    __syncwarp();
+    if (c.lane == 0) {
+        const uint32_t old = stat[leaf].w;
+        stat[leaf].w = (old & 0xF0000000u) | ((uint32_t)b << 22) | (uint32_t)fc;
+        S.alloc[t] = fc + b;
+        S.pend_leaf = -1;
+        S.tot_evals += 1; S.tot_sims += 1; S.sims_done += 1;
+        atomicAdd(&E.ctr->nodes, (unsigned long long)b);
+    }
+    __syncwarp();
+    backup(c, S.pend_depth, false, 0, value, lplayer);
+}
+
+// K5: copy the subtree under `root` of tree t into the scratch buffer in BFS order and make
+// the scratch buffer the tree's buffer.  32 nodes per iteration: each lane relocates the
+// child block of one node; block positions come from a warp prefix sum.
+__device__ void compact_tree(const WarpCtx &c, int t, int root) {
+    Slot &S = c.S;
+    const uint4 *spos = c.pos_of(t), *sstat = c.stat_of(t);
+    uint4 *dpos = c.pos_buf(S.scratch), *dstat = c.stat_buf(S.scratch);
+    if (c.lane == 0) { dpos[0] = spos[root]; dstat[0] = sstat[root]; }
+    __syncwarp();
+    int count = 1;
+    for (int head = 0; head < count; head += 32) {
+        const int i = head + c.lane;
+        const bool valid = i < count;
+        const uint32_t link = valid ? dstat[i].w : 0u;
+        const int nch = link_nchild(link), ofc = (int)(link & kFcMask);
+        int incl = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(CK_FULL, incl, o);
+            if (c.lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(CK_FULL, incl, 31);
+        const int nfc = count + incl - nch;
+        if (nch > 0) {
+            for (int k = 0; k < nch; ++k) { dpos[nfc + k] = spos[ofc + k]; dstat[nfc + k] = sstat[ofc + k]; }
+            dstat[i].w = (link & ~kFcMask) | (uint32_t)nfc;
+        }
+        count += total;
+        __syncwarp();
+    }
+    __syncwarp();
+    if (c.lane == 0) {
+        const int old = S.buf[t];
+        S.buf[t] = S.scratch; S.scratch = old;
+        S.root[t] = 0; S.alloc[t] = count;
+        atomicAdd(&c.E.ctr->compactions, 1ull);
+    }
+    __syncwarp();
+}
+
+// Root of the coming search: first search of a colour builds a fresh root
+// (training_pipeline.py:353,371-373), later ones re-root the colour's own tree through the
+// states played since its last move (MCTS.new_root_node, MCTS.py:250-295).
+__device__ void setup_root(const WarpCtx &c) {
+    const EngineDev &E = c.E;
+    Slot &S = c.S;
+    const int L = S.hist_len;
+    const ck_pos cur = c.hist[L - 1];
+    const int t = meta_player(cur.meta);
+    const int parent_player = L >= 2 ? meta_player(c.hist[L - 2].meta) : 1 - t;   // MCTS.py:167-173
+    bool fresh = !S.exists[t];
+    if (!fresh) {
+        const uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
+        int counter = 1;
+        for (int idx = L - 3; idx >= 0 && meta_player(c.hist[L - 2].meta) == meta_player(c.hist[idx].meta); --idx) ++counter;
+        int nr = S.best[t];
+        for (int i = L - counter; i < L; ++i) {
+            const ck_pos want = c.hist[i];
+            const uint32_t link = stat[nr].w;
+            const int b = link_nchild(link), fc = (int)(link & kFcMask);
+            int found = kNoIdx;
+            for (int j = c.lane; j < b; j += 32)
+                if (found == kNoIdx && same_state(to_pos(pos[fc + j]), want)) found = j;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) found = min(found, __shfl_xor_sync(CK_FULL, found, o));
+            if (found != kNoIdx) nr = fc + found;
+        }
+        if (same_state(to_pos(pos[nr]), cur)) {
+            __syncwarp();
+            if (c.lane == 0) {
+                S.root[t] = nr;
+                uint4 *wstat = c.stat_of(t);
+                wstat[nr].w = (wstat[nr].w & ~(1u << 30)) | ((uint32_t)parent_player << 30);
+            }
+            __syncwarp();
+            if (E.cap - S.alloc[t] < E.compact_need || E.cfg.compact_always) compact_tree(c, t, nr);
+        } else {
+            // the reference raises here (MCTS.py:292); the dead code after the raise shows the
+            // intent -- a fresh root.  Counted, never silent.
+            fresh = true;
+            __syncwarp();
+            if (c.lane == 0) S.misses += 1;
+        }
+    }
+    if (fresh) {
+        __syncwarp();
+        if (c.lane == 0) {
+            uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
+            pos[0] = from_pos(cur);
+            stat[0] = make_uint4(0u, __float_as_uint(0.f), __float_as_uint(0.f), (uint32_t)parent_player << 30);
+            S.root[t] = 0; S.alloc[t] = 1; S.exists[t] = 1;
+            atomicAdd(&E.ctr->nodes, 1ull);
+        }
+    }
+    __syncwarp();
+    if (c.lane == 0) { S.cur = t; S.phase = PH_SEARCH; S.sims_done = 0; S.search_id += 1; }
+    __syncwarp();
+}
+
+__device__ void init_game(const WarpCtx &c, int local_game) {
+    Slot &S = c.S;
+    __syncwarp();
+    if (c.lane == 0) {
+        S.game = local_game;
+        S.hist_len = 1; S.move_count = 0; S.phase = PH_NEED_ROOT; S.cur = 0; S.sims_done = 0;
+        S.pend_leaf = -1;
+        S.buf[0] = 0; S.buf[1] = 1; S.scratch = 2;
+        S.exists[0] = S.exists[1] = 0;
+        S.nrec = 0; S.misses = 0; S.search_id = 0; S.g_sims0 = S.tot_sims; S.g_evals0 = S.tot_evals;
+        if (!c.E.cfg.reference_tau_quirk || S.tau < -1e300) S.tau = c.E.cfg.tau;
+        c.hist[0] = start_position();
+    }
+    __syncwarp();
+}
+
+// take the next staged game or go idle
+__device__ bool refill(const WarpCtx &c) {
+    int g = -1;
+    if (c.lane == 0 && *(volatile int32_t *)&c.E.ctr->next_game < c.E.n_games) {
+        g = atomicAdd(&c.E.ctr->next_game, 1);
+        if (g >= c.E.n_games) g = -1;
+    }
+    g = __shfl_sync(CK_FULL, g, 0);
+    __syncwarp();
+    if (g < 0) { if (c.lane == 0) c.S.game = -1; __syncwarp(); return false; }
+    init_game(c, g);
+    return true;
+}
+
+// K6: MCTS.best_child (MCTS.py:226-248) + the game loop body after a search
+// (training_pipeline.py:362-411): record, step, TERMINATE_CNT adjudication, terminal record,
+// rewards.  Returns false when the slot went idle.
+__device__ bool play_move(const WarpCtx &c) {
+    const EngineDev &E = c.E;
+    Slot &S = c.S;
+    const int t = S.cur;
+    uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
+    const int root = S.root[t];
+    const uint4 rst = stat[root];
+    const ck_pos rpos = to_pos(pos[root]);
+    const int b = link_nchild(rst.w), fc = (int)(rst.w & kFcMask);
+    const int parent_player = link_pp(rst.w);
+    uint32_t n0 = 0, n1 = 0;
+    ck_pos k0 = rpos, k1 = rpos;
+    uint32_t l0 = 0, l1 = 0;
+    if (c.lane < b) { const uint4 s = stat[fc + c.lane]; n0 = s.x; l0 = s.w; k0 = to_pos(pos[fc + c.lane]); }
+    if (c.lane + 32 < b) { const uint4 s = stat[fc + 32 + c.lane]; n1 = s.x; l1 = s.w; k1 = to_pos(pos[fc + 32 + c.lane]); }
+    int best;
+    if (!E.cfg.training || S.tau <= 0.0) {              // argmax visits, first maximum (:236-238)
+        long long key = -1;
+        if (c.lane < b) key = ((long long)n0 << 8) | (long long)(255 - c.lane);
+        if (c.lane + 32 < b) { const long long k2 = ((long long)n1 << 8) | (long long)(255 - (c.lane + 32)); if (k2 > key) key = k2; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const long long ok = __shfl_xor_sync(CK_FULL, key, o); if (ok > key) key = ok; }
+        best = 255 - (int)(key & 255);
+    } else {                                             // sample ~ n^(1/tau) (:239-246)
+        const double inv = 1.0 / S.tau;
+        const double e0 = c.lane < b ? pow((double)n0, inv) : 0.0;
+        const double e1 = c.lane + 32 < b ? pow((double)n1, inv) : 0.0;
+        double s0 = e0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = shfl_up_d(s0, o); if (c.lane >= o) s0 += v; }
+        const double tot0 = shfl_d(s0, 31);
+        double s1 = e1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = shfl_up_d(s1, o); if (c.lane >= o) s1 += v; }
+        const double total = tot0 + shfl_d(s1, 31);
+        s1 += tot0;
+        uint32_t r[4];
+        Philox(game_key(E, S.game))((uint32_t)S.search_id, 0xFFFFFFFFu, 0u, 0x54415521u, r);
+        const double u = u01(r[0], r[1]) * total;
+        int pick = kNoIdx;
+        if (c.lane < b && u <= s0) pick = c.lane;
+        if (pick == kNoIdx && c.lane + 32 < b && u <= s1) pick = c.lane + 32;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) pick = min(pick, __shfl_xor_sync(CK_FULL, pick, o));
+        best = pick == kNoIdx ? b - 1 : pick;
+        __syncwarp();
+        if (c.lane == 0 && S.move_count > E.cfg.tau_decay_delay) {
+            double tau = S.tau - E.cfg.tau_decay;
+            if (fabs(tau) <= 1e-8) tau = 0.0;           // np.isclose(tau, 0)
+            S.tau = tau;
+        }
+    }
+    const ck_pos bpos = best < 32 ? to_pos(shfl4(from_pos(k0), best)) : to_pos(shfl4(from_pos(k1), best - 32));
+    const uint32_t blink = best < 32 ? __shfl_sync(CK_FULL, l0, best) : __shfl_sync(CK_FULL, l1, best - 32);
+    const int bstatus = link_status(blink);
+    const int gg = global_game(E, S.game);
+    // record [root.state, visit planes, q] (:364-369)
+    ck_record *rec = nullptr;
+    if (E.cfg.keep_records && S.nrec < E.max_rec) rec = E.rec + (int64_t)S.game * E.max_rec + S.nrec;
+    if (rec) {
+        if (c.lane < b) { rec->action[c.lane] = (uint16_t)meta_action(k0.meta); rec->visits[c.lane] = n0; }
+        if (c.lane + 32 < b) { rec->action[c.lane + 32] = (uint16_t)meta_action(k1.meta); rec->visits[c.lane + 32] = n1; }
+        if (c.lane == 0) {
+            int p5;
+            const int cnt = gen_moves(rpos, NullSink{}, rec->mask);
+            outcome_of(rpos, cnt > 0, &p5);
+            rec->pos = rpos; rec->plane5 = p5; rec->n_children = b;
+            const float q = rst.x ? __fdiv_rn(__uint_as_float(rst.y), (float)rst.x) : 0.f;
+            rec->q = parent_player != meta_player(rpos.meta) ? -q : q;
+            rec->z = 0; rec->root_n = rst.x; rec->root_w = __uint_as_float(rst.y);
+            rec->chosen = meta_action(bpos.meta); rec->game = gg; rec->ply = S.nrec;
+        }
+    }
+    bool done = false, terminated = false;
+    int outcome = CK_ONGOING;
+    __syncwarp();
+    if (c.lane == 0) {
+        if (rec) S.nrec += 1;
+        S.best[t] = fc + best;
+        if (S.hist_len <= E.max_plies) { c.hist[S.hist_len] = bpos; S.hist_len += 1; }
+        else dev_error(E, CK_ERR_STATE);
+        S.move_count += 1;
+        atomicAdd(&E.ctr->moves, 1ull);
+    }
+    __syncwarp();
+    if (bstatus != CK_ONGOING) { done = true; outcome = bstatus; }
+    if (!done && E.cfg.terminate_cnt > 0 && S.move_count >= E.cfg.terminate_cnt) {   // (:387-405)
+        done = true; terminated = true;
+        const int p1 = popc32(bpos.p1), p2 = popc32(bpos.p2);
+        const int q1 = popc32(bpos.p1 & bpos.k), q2 = popc32(bpos.p2 & bpos.k);
+        outcome = p1 > p2 ? CK_P1_WINS : p1 < p2 ? CK_P2_WINS : q1 > q2 ? CK_P1_WINS : q1 < q2 ? CK_P2_WINS : CK_DRAW;
+    }
+    if (!done) {
+        if (c.lane == 0) S.phase = PH_NEED_ROOT;
+        __syncwarp();
+        return true;
+    }
+    __syncwarp();
+    if (!terminated && E.cfg.keep_records && S.nrec < E.max_rec && c.lane == 0) {    // terminal record (:406-409)
+        ck_record *tr = E.rec + (int64_t)S.game * E.max_rec + S.nrec;
+        int p5;
+        const int cnt = gen_moves(bpos, NullSink{}, tr->mask);
+        outcome_of(bpos, cnt > 0, &p5);
+        tr->pos = bpos; tr->plane5 = p5; tr->n_children = 0;
+        tr->q = outcome == CK_DRAW ? 0.f : -1.f;
+        tr->z = 0; tr->root_n = 0; tr->root_w = 0.f; tr->chosen = -1; tr->game = gg; tr->ply = S.nrec;
+        S.nrec += 1;
+    }
+    __syncwarp();
+    if (E.cfg.keep_records) {                            // _add_rewards (:439-455)
+        ck_record *base = E.rec + (int64_t)S.game * E.max_rec;
+        for (int i = c.lane; i < S.nrec; i += 32) {
+            const int pl = meta_player(base[i].pos.meta);
+            base[i].z = outcome == CK_P1_WINS ? (pl == 0 ? 1 : -1) : outcome == CK_P2_WINS ? (pl == 1 ? 1 : -1) : 0;
+        }
+    }
+    if (c.lane == 0) {
+        ck_game_result &r = E.results[S.game];
+        r.game = gg; r.outcome = outcome; r.move_count = S.move_count; r.terminated = terminated ? 1 : 0;
+        r.n_records = S.nrec; r.reroot_misses = S.misses;
+        r.p1_net = net_of(E, S.game, 0); r.reserved = 0;
+        r.sims = S.tot_sims - S.g_sims0; r.nn_evals = S.tot_evals - S.g_evals0;
+        __threadfence();
+        atomicAdd(&E.ctr->games_finished, 1ull);
+    }
+    __syncwarp();
+    return refill(c);
+}
+
+// ---- the per-round tree kernel ------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+tree_step_kernel(const EngineDev E) {
+    __shared__ Slot s_slot[kWarpsPerBlock];
+    __shared__ ck_pos s_kids[kWarpsPerBlock][CK_MAX_CHILDREN];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * kWarpsPerBlock + w;
+    if (slot >= E.n_slots) return;
+    Slot &S = s_slot[w];
+    {
+        const int *src = reinterpret_cast<const int *>(E.slots + slot);
+        int *dst = reinterpret_cast<int *>(&S);
+        for (int i = lane; i < (int)(sizeof(Slot) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    WarpCtx c{E, S, s_kids[w], E.path + (int64_t)slot * kMaxDepth, E.hist + (int64_t)slot * (E.max_plies + 1), slot, lane};
+    bool live = true;
+    if (E.ctr->error != 0) live = false;
+    if (live && S.game < 0) live = S.manual ? false : refill(c);
+    if (live && S.phase == PH_HALT) live = false;
+    if (live && S.pend_leaf >= 0) expand_pending(c);
+    int term_iters = 0;
+    const int max_term = E.max_term;
+    while (live && S.phase != PH_HALT) {
+        if (S.phase == PH_NEED_ROOT) setup_root(c);
+        const int target = S.manual ? S.manual_target : E.cfg.budget;
+        if (S.sims_done >= target) {                     // MCTS.computational_budget (MCTS.py:196-198)
+            if (S.manual) { __syncwarp(); if (lane == 0) S.phase = PH_HALT; __syncwarp(); break; }
+            if (!play_move(c)) { live = false; break; }
+            continue;
+        }
+        int depth = 0;
+        const int leaf = select_leaf(c, &depth);
+        if (leaf >= 0) { stage_leaf(c, leaf, depth); break; }
+        __syncwarp();
+        if (leaf == -2) { if (lane == 0) S.phase = PH_HALT; __syncwarp(); break; }
+        if (lane == 0) { S.tot_sims += 1; S.sims_done += 1; }
+        __syncwarp();
+        if (++term_iters >= max_term) break;
+    }
+    if (lane == 0 && S.game >= 0 && S.phase != PH_HALT) atomicAdd(&E.ctr->active, 1);
+    __syncwarp();
+    {
+        int *dst = reinterpret_cast<int *>(E.slots + slot);
+        const int *src = reinterpret_cast<const int *>(&S);
+        for (int i = lane; i < (int)(sizeof(Slot) / 4); i += 32) dst[i] = src[i];
+    }
+}
+
+// simulation / evaluation totals live per slot (no hot-path atomics); summed on demand
+__global__ void sum_slots_kernel(const EngineDev E, unsigned long long *out_sims, unsigned long long *out_evals) {
+    unsigned long long s = 0, e = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E.n_slots; i += gridDim.x * blockDim.x) {
+        s += E.slots[i].tot_sims; e += E.slots[i].tot_evals;
+    }
+    atomicAdd(out_sims, s); atomicAdd(out_evals, e);
+}
+
+// ---- stub evaluators (deterministic parity tests; twins of the oracle's cko_eval_*) ----------
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+__global__ void __launch_bounds__(128)
+stub_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restrict__ n_dev, int kind,
+                 float *__restrict__ policy, float *__restrict__ value) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= *n_dev) return;
+    const ck_leaf L = leaves[row];
+    float *dst = policy + (int64_t)row * CK_POLICY_SIZE;
+    if (kind == CK_EVAL_HASH || kind == CK_EVAL_HASH_SALTED) {
+        const uint32_t p5 = (L.info >> 8) & 0xFFu;
+        const uint32_t salt = kind == CK_EVAL_HASH_SALTED ? (L.info >> 16) : 0u;
+        uint32_t h = mix32(L.p1 ^ 0x9e3779b9u ^ (salt * 0x9E3779B1u));
+        h = mix32(h ^ L.p2);
+        h = mix32(h ^ L.k);
+        h = mix32(h ^ (L.info & 1u) ^ (p5 << 8));
+        for (int i = lane; i < CK_POLICY_SIZE; i += 32) {
+            const uint32_t g = mix32(h + (uint32_t)i * 0x85ebca6bu);
+            const float v = __fadd_rn((float)((g >> 8) & 0xFFFFu), 1.0f);
+            dst[i] = __fmul_rn(__fmul_rn(__fmul_rn(v, v), v), 0x1p-58f);
+        }
+        if (lane == 0) {
+            const uint32_t g = mix32(h ^ 0xdeadbeefu);
+            value[row] = __fsub_rn(__fmul_rn((float)(g & 0xFFFFFFu), 0x1p-23f), 1.0f);
+        }
+    } else {
+        for (int i = lane; i < CK_POLICY_SIZE; i += 32) dst[i] = 1.0f / 512.0f;
+        if (lane == 0) {
+            float v = 0.f;
+            if (kind == CK_EVAL_UNIFORM_MATERIAL) {
+                const int a = __popc(L.p1) + __popc(L.p1 & L.k), b = __popc(L.p2) + __popc(L.p2 & L.k);
+                v = __fdiv_rn((float)((L.info & 1u) == 0 ? a - b : b - a), 32.0f);
+            }
+            value[row] = v;
+        }
+    }
+}
+
+}  // namespace ck
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace ck;
+
+struct ck_engine {
+    EngineDev dev;           // device pointers + config, passed by value to the kernels
+    ck_net *net[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+    Counters *h_ctr = nullptr;        // pinned
+    int64_t n_games = 0;
+    size_t rec_cap = 0, res_cap = 0;
+    bool profile = false;
+    bool begun = false;
+    uint64_t total_steps = 0;
+};
+
+static void engine_free(ck_engine *e) {
+    if (!e) return;
+    EngineDev &d = e->dev;
+    cudaFree(d.pos); cudaFree(d.stat); cudaFree(d.hist); cudaFree(d.path); cudaFree(d.slots); cudaFree(d.ctr);
+    for (int k = 0; k < 2; ++k) { cudaFree(d.leaves[k]); cudaFree(d.policy[k]); cudaFree(d.value[k]); }
+    cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half);
+    if (e->h_ctr) cudaFreeHost(e->h_ctr);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->evp0) cudaEventDestroy(e->evp0);
+    if (e->evp1) cudaEventDestroy(e->evp1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+#define CK_E(expr)                                                                           \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ck::fail(CK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+            engine_free(e);                                                                  \
+            return nullptr;                                                                  \
+        }                                                                                    \
+    } while (0)
+
+extern "C" {
+
+ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
+    if (!cfg || cfg->n_slots < 1 || cfg->budget < 1) { fail(CK_ERR_ARG, "ck_engine_create: n_slots and budget must be >= 1"); return nullptr; }
+    DeviceGuard g(cfg->device);
+    if (!g.ok) { fail(CK_ERR_CUDA, "ck_engine_create: cannot select CUDA device " + std::to_string(cfg->device)); return nullptr; }
+    ck_engine *e = new ck_engine();
+    EngineDev &d = e->dev;
+    memset(&d, 0, sizeof(d));
+    d.cfg = *cfg;
+    d.n_slots = cfg->n_slots;
+    d.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 2048;
+    int cap = cfg->pool_cap;
+    if (cap <= 0) { cap = 32768; while (cap < 3 * cfg->budget * 24) cap *= 2; }
+    if (cap > (int)kFcMask) cap = (int)kFcMask;
+    d.cap = cap;
+    int need = cfg->budget * CK_MAX_CHILDREN;            // room for a whole search in the worst case
+    if (need > cap / 2) need = cap / 2;
+    d.compact_need = need;
+    d.max_term = cfg->max_terminal_sims_per_step > 0 ? cfg->max_terminal_sims_per_step : 64;
+    d.one_minus_eps = (float)(1.0 - cfg->epsilon);       // (1 - eps) * float32 array stays float32 (numpy >= 2)
+    if (cfg->keep_records) d.max_rec = (cfg->terminate_cnt > 0 ? cfg->terminate_cnt : d.max_plies) + 1;
+    CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK_E(cudaEventCreate(&e->ev0)); CK_E(cudaEventCreate(&e->ev1));
+    CK_E(cudaEventCreate(&e->evp0)); CK_E(cudaEventCreate(&e->evp1));
+    const size_t nodes = (size_t)d.n_slots * 3 * d.cap;
+    CK_E(cudaMalloc(&d.pos, nodes * sizeof(uint4)));
+    CK_E(cudaMalloc(&d.stat, nodes * sizeof(uint4)));
+    CK_E(cudaMalloc(&d.hist, (size_t)d.n_slots * (d.max_plies + 1) * sizeof(ck_pos)));
+    CK_E(cudaMalloc(&d.path, (size_t)d.n_slots * kMaxDepth * sizeof(uint32_t)));
+    CK_E(cudaMalloc(&d.slots, (size_t)d.n_slots * sizeof(Slot)));
+    CK_E(cudaMalloc(&d.ctr, sizeof(Counters)));
+    CK_E(cudaMemset(d.ctr, 0, sizeof(Counters)));
+    for (int k = 0; k < (cfg->arena ? 2 : 1); ++k) {
+        CK_E(cudaMalloc(&d.leaves[k], (size_t)d.n_slots * sizeof(ck_leaf)));
+        CK_E(cudaMalloc(&d.policy[k], (size_t)d.n_slots * CK_POLICY_SIZE * sizeof(float)));
+        CK_E(cudaMalloc(&d.value[k], (size_t)d.n_slots * sizeof(float)));
+    }
+    CK_E(cudaMallocHost(&e->h_ctr, sizeof(Counters)));
+    {
+        // node.n ** 0.5 is libm pow in the reference (MCTS.py:110) and differs from sqrt for
+        // some integers; the table is built with the host's libm so the two agree.
+        std::vector<double> tab(kPowTable);
+        for (int i = 0; i < kPowTable; ++i) tab[i] = pow((double)i, 0.5);
+        double *p = nullptr;
+        CK_E(cudaMalloc(&p, kPowTable * sizeof(double)));
+        d.pow_half = p;
+        CK_E(cudaMemcpy(p, tab.data(), kPowTable * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<Slot> init(d.n_slots);
+        memset(init.data(), 0, init.size() * sizeof(Slot));
+        for (auto &s : init) { s.game = -1; s.pend_leaf = -1; s.tau = -1e301; s.phase = PH_NEED_ROOT; }
+        CK_E(cudaMemcpy(d.slots, init.data(), init.size() * sizeof(Slot), cudaMemcpyHostToDevice));
+    }
+    return e;
+}
+
+void ck_engine_destroy(ck_engine *e) {
+    if (!e) return;
+    DeviceGuard g(e->dev.cfg.device);
+    cudaDeviceSynchronize();
+    engine_free(e);
+}
+
+int ck_engine_set_net(ck_engine *e, int which, ck_net *net) {
+    if (!e || which < 0 || which > 1 || !net) return fail(CK_ERR_ARG, "ck_engine_set_net: bad arguments");
+    if (net->device != e->dev.cfg.device) return fail(CK_ERR_ARG, "ck_engine_set_net: net lives on another device");
+    e->net[which] = net;
+    return CK_OK;
+}
+
+int ck_engine_set_profile(ck_engine *e, int on) {
+    if (!e) return fail(CK_ERR_ARG, "ck_engine_set_profile: null engine");
+    e->profile = on != 0;
+    return CK_OK;
+}
+
+static int engine_reset_slots(ck_engine *e, int manual) {
+    EngineDev &d = e->dev;
+    std::vector<Slot> init(d.n_slots);
+    memset(init.data(), 0, init.size() * sizeof(Slot));
+    for (auto &s : init) { s.game = -1; s.pend_leaf = -1; s.tau = -1e301; s.phase = PH_NEED_ROOT; s.manual = manual; }
+    CK_CUDA(cudaMemcpyAsync(d.slots, init.data(), init.size() * sizeof(Slot), cudaMemcpyHostToDevice, e->stream));
+    CK_CUDA(cudaMemsetAsync(d.ctr, 0, sizeof(Counters), e->stream));
+    CK_CUDA(cudaStreamSynchronize(e->stream));
+    return CK_OK;
+}
+
+int ck_engine_begin(ck_engine *e, int64_t n_games) {
+    if (!e || n_games < 1 || n_games > (1 << 30)) return fail(CK_ERR_ARG, "ck_engine_begin: bad n_games");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    if (d.cfg.evaluator == CK_EVAL_NET) {
+        for (int k = 0; k < (d.cfg.arena ? 2 : 1); ++k)
+            if (!e->net[k] || !e->net[k]->have_weights) return fail(CK_ERR_NO_NET, "ck_engine_begin: evaluator is the network but no weights are attached");
+    }
+    if ((size_t)n_games > e->res_cap) {
+        cudaFree(d.results); d.results = nullptr; e->res_cap = 0;
+        CK_CUDA(cudaMalloc(&d.results, (size_t)n_games * sizeof(ck_game_result)));
+        e->res_cap = (size_t)n_games;
+    }
+    if (d.cfg.keep_records && (size_t)n_games * d.max_rec > e->rec_cap) {
+        cudaFree(d.rec); d.rec = nullptr; e->rec_cap = 0;
+        CK_CUDA(cudaMalloc(&d.rec, (size_t)n_games * d.max_rec * sizeof(ck_record)));
+        e->rec_cap = (size_t)n_games * d.max_rec;
+    }
+    CK_CUDA(cudaMemsetAsync(d.results, 0xFF, (size_t)n_games * sizeof(ck_game_result), e->stream));
+    d.n_games = (int32_t)n_games;
+    const int stride = d.cfg.game_id_stride ? d.cfg.game_id_stride : 1;
+    d.arena_half = (int32_t)((n_games * stride) / 2);
+    e->n_games = n_games;
+    int rc = engine_reset_slots(e, 0);
+    if (rc != CK_OK) return rc;
+    e->begun = true;
+    return CK_OK;
+}
+
+static int engine_eval(ck_engine *e, int *launches) {
+    EngineDev &d = e->dev;
+    for (int k = 0; k < (d.cfg.arena ? 2 : 1); ++k) {
+        int kind = d.cfg.evaluator;
+        if (k == 1 && d.cfg.evaluator_p2 >= 0) kind = d.cfg.evaluator_p2;
+        if (kind == CK_EVAL_NET) {
+            int rc = net_forward_rows(e->net[k], d.leaves[k], d.n_slots, &d.ctr->batch_count[k], d.policy[k], d.value[k], e->stream, launches);
+            if (rc != CK_OK) return rc;
+        } else {
+            stub_eval_kernel<<<(d.n_slots * 32 + 127) / 128, 128, 0, e->stream>>>(d.leaves[k], &d.ctr->batch_count[k], kind, d.policy[k], d.value[k]);
+            if (launches) *launches += 1;
+        }
+    }
+    return CK_OK;
+}
+
+// One lock-step round = tree kernel + evaluation of the staged leaves.
+static int engine_round(ck_engine *e, int *launches) {
+    EngineDev &d = e->dev;
+    CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));   // active + batch_count[2]
+    tree_step_kernel<<<(d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+    if (launches) *launches += 1;
+    CK_CUDA(cudaGetLastError());
+    return engine_eval(e, launches);
+}
+
+static int engine_poll(ck_engine *e) {
+    CK_CUDA(cudaMemcpyAsync(e->h_ctr, e->dev.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+    CK_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_ctr->error != 0) {
+        const int code = e->h_ctr->error;
+        return fail(code, code == CK_ERR_POOL_OVERFLOW ? "engine: node pool overflow (raise pool_cap)" :
+                          code == CK_ERR_DEPTH ? "engine: tree deeper than 128 plies" : "engine: device-side state error (history capacity?)");
+    }
+    return CK_OK;
+}
+
+int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
+    if (!e || !e->begun) return fail(CK_ERR_STATE, "ck_engine_run: call ck_engine_begin first");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    int rc = engine_poll(e);
+    if (rc != CK_OK) return rc;
+    const Counters before = *e->h_ctr;
+    unsigned long long *d_tot = nullptr;
+    CK_CUDA(cudaMalloc(&d_tot, 4 * sizeof(unsigned long long)));
+    CK_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), e->stream));
+    sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot, d_tot + 1);
+    int launches = 0;
+    float eval_ms = 0.f;
+    CK_CUDA(cudaEventRecord(e->ev0, e->stream));
+    int64_t steps = 0;
+    const int check = 16;
+    for (;;) {
+        const int64_t chunk = n_steps > 0 ? std::min<int64_t>(check, n_steps - steps) : check;
+        for (int64_t i = 0; i < chunk; ++i) {
+            if (e->profile) {
+                CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));
+                tree_step_kernel<<<(d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+                ++launches;
+                CK_CUDA(cudaEventRecord(e->evp0, e->stream));
+                rc = engine_eval(e, &launches);
+                if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+                CK_CUDA(cudaEventRecord(e->evp1, e->stream));
+                CK_CUDA(cudaEventSynchronize(e->evp1));
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e->evp0, e->evp1);
+                eval_ms += ms;
+            } else {
+                rc = engine_round(e, &launches);
+                if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+            }
+        }
+        steps += chunk;
+        rc = engine_poll(e);
+        if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+        if (n_steps > 0 && steps >= n_steps) break;
+        if (n_steps <= 0 && e->h_ctr->active == 0 && e->h_ctr->batch_count[0] == 0 && e->h_ctr->batch_count[1] == 0) break;
+        if (n_steps <= 0 && e->h_ctr->games_finished >= (unsigned long long)e->n_games) break;
+    }
+    CK_CUDA(cudaEventRecord(e->ev1, e->stream));
+    sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot + 2, d_tot + 3);
+    unsigned long long tot[4];
+    CK_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, e->stream));
+    CK_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(d_tot);
+    e->total_steps += (uint64_t)steps;
+    if (stats) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+        memset(stats, 0, sizeof(*stats));
+        const Counters &now = *e->h_ctr;
+        stats->steps = (uint64_t)steps;
+        stats->games_finished = now.games_finished - before.games_finished;
+        stats->moves = now.moves - before.moves;
+        stats->nodes_created = now.nodes - before.nodes;
+        stats->compactions = now.compactions - before.compactions;
+        stats->gpu_ms = ms;
+        stats->eval_ms = eval_ms;
+        stats->kernel_launches = (uint64_t)launches;
+        stats->sims = tot[2] - tot[0]; stats->nn_evals = tot[3] - tot[1];
+    }
+    return CK_OK;
+}
+
+
+int ck_selfplay_run(ck_engine *e, int64_t n_games, ck_run_stats *stats) {
+    if (!e) return fail(CK_ERR_ARG, "ck_selfplay_run: null engine");
+    if (e->dev.cfg.arena) return fail(CK_ERR_ARG, "ck_selfplay_run: engine was created for arena play");
+    int rc = ck_engine_begin(e, n_games);
+    if (rc != CK_OK) return rc;
+    return ck_engine_run(e, 0, stats);
+}
+
+int ck_arena_run(ck_engine *e, int64_t n_games, ck_run_stats *stats) {
+    if (!e) return fail(CK_ERR_ARG, "ck_arena_run: null engine");
+    if (!e->dev.cfg.arena) return fail(CK_ERR_ARG, "ck_arena_run: engine was created for self-play");
+    int rc = ck_engine_begin(e, n_games);
+    if (rc != CK_OK) return rc;
+    return ck_engine_run(e, 0, stats);
+}
+
+int64_t ck_games_finished(ck_engine *e) {
+    if (!e || !e->begun) return 0;
+    DeviceGuard g(e->dev.cfg.device);
+    if (engine_poll(e) != CK_OK) return -1;
+    return (int64_t)e->h_ctr->games_finished;
+}
+
+// finished games in local game order (unfinished ones are skipped)
+int ck_games_fetch(ck_engine *e, ck_game_result *out, int64_t cap) {
+    if (!e || !e->begun || !out) return fail(CK_ERR_ARG, "ck_games_fetch: bad arguments");
+    DeviceGuard g(e->dev.cfg.device);
+    std::vector<ck_game_result> all((size_t)e->n_games);
+    CK_CUDA(cudaMemcpy(all.data(), e->dev.results, all.size() * sizeof(ck_game_result), cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    for (const ck_game_result &r : all) {
+        if (r.game < 0 || r.outcome < 0) continue;
+        if (k < cap) out[k] = r;
+        ++k;
+    }
+    return k <= cap ? CK_OK : fail(CK_ERR_ARG, "ck_games_fetch: buffer too small");
+}
+
+int64_t ck_records_count(ck_engine *e) {
+    if (!e || !e->begun || !e->dev.cfg.keep_records) return 0;
+    DeviceGuard g(e->dev.cfg.device);
+    std::vector<ck_game_result> all((size_t)e->n_games);
+    if (cudaMemcpy(all.data(), e->dev.results, all.size() * sizeof(ck_game_result), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t k = 0;
+    for (const ck_game_result &r : all) if (r.game >= 0 && r.outcome >= 0) k += r.n_records;
+    return k;
+}
+
+// records of all finished games, game by game in local game order, plies in order
+int ck_records_fetch(ck_engine *e, ck_record *out, int64_t cap) {
+    if (!e || !e->begun || !out) return fail(CK_ERR_ARG, "ck_records_fetch: bad arguments");
+    if (!e->dev.cfg.keep_records) return fail(CK_ERR_STATE, "ck_records_fetch: engine was created with keep_records = 0");
+    DeviceGuard g(e->dev.cfg.device);
+    std::vector<ck_game_result> all((size_t)e->n_games);
+    CK_CUDA(cudaMemcpy(all.data(), e->dev.results, all.size() * sizeof(ck_game_result), cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    for (size_t gi = 0; gi < all.size(); ++gi) {
+        const ck_game_result &r = all[gi];
+        if (r.game < 0 || r.outcome < 0) continue;
+        if (k + r.n_records > cap) return fail(CK_ERR_ARG, "ck_records_fetch: buffer too small");
+        CK_CUDA(cudaMemcpy(out + k, e->dev.rec + gi * e->dev.max_rec, (size_t)r.n_records * sizeof(ck_record), cudaMemcpyDeviceToHost));
+        k += r.n_records;
+    }
+    return CK_OK;
+}
+
+// ---- single-search API (slot 0) -----------------------------------------------------------
+static int manual_slot(ck_engine *e, Slot *s) {
+    CK_CUDA(cudaMemcpy(s, e->dev.slots, sizeof(Slot), cudaMemcpyDeviceToHost));
+    if (!s->manual || s->game < 0) return fail(CK_ERR_STATE, "ck_tree_*: call ck_tree_set_root first");
+    return CK_OK;
+}
+
+int ck_tree_set_root(ck_engine *e, const ck_pos *root, int32_t parent_player) {
+    if (!e || !root) return fail(CK_ERR_ARG, "ck_tree_set_root: bad arguments");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    if (d.cfg.evaluator == CK_EVAL_NET && (!e->net[0] || !e->net[0]->have_weights))
+        return fail(CK_ERR_NO_NET, "ck_tree_set_root: evaluator is the network but no weights are attached");
+    if (e->res_cap < 1) {
+        CK_CUDA(cudaMalloc(&d.results, sizeof(ck_game_result)));
+        e->res_cap = 1;
+    }
+    d.n_games = 1; e->n_games = 1; d.arena_half = 1;
+    int rc = engine_reset_slots(e, 1);
+    if (rc != CK_OK) return rc;
+    Slot s;
+    memset(&s, 0, sizeof(s));
+    const int player = (int)(root->meta & 1u);
+    s.game = 0; s.manual = 1; s.manual_target = 0; s.pend_leaf = -1;
+    s.phase = PH_NEED_ROOT; s.cur = player; s.tau = d.cfg.tau;
+    s.buf[0] = 0; s.buf[1] = 1; s.scratch = 2;
+    // history = [dummy previous state with the wanted parent player, root]
+    ck_pos hist[2];
+    hist[0] = *root;
+    const int pp = parent_player >= 0 ? parent_player : 1 - player;
+    hist[0].meta = (root->meta & ~1u) | (uint32_t)pp;
+    hist[0].p1 = hist[0].p2 = hist[0].k = 0;
+    hist[1] = *root;
+    s.hist_len = 2;
+    CK_CUDA(cudaMemcpy(d.hist, hist, sizeof(hist), cudaMemcpyHostToDevice));
+    CK_CUDA(cudaMemcpy(d.slots, &s, sizeof(Slot), cudaMemcpyHostToDevice));
+    e->begun = true;
+    return CK_OK;
+}
+
+int ck_tree_search(ck_engine *e, int32_t sims) {
+    if (!e || sims < 0) return fail(CK_ERR_ARG, "ck_tree_search: bad arguments");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    Slot s;
+    int rc = manual_slot(e, &s);
+    if (rc != CK_OK) return rc;
+    s.manual_target = sims; s.sims_done = 0;       // BUDGET new simulations on top of inherited statistics (MCTS.py:217)
+    if (s.phase == PH_HALT) s.phase = PH_SEARCH;
+    CK_CUDA(cudaMemcpy(d.slots, &s, sizeof(Slot), cudaMemcpyHostToDevice));
+    for (;;) {
+        for (int i = 0; i < 16; ++i) { rc = engine_round(e, nullptr); if (rc != CK_OK) return rc; }
+        rc = engine_poll(e);
+        if (rc != CK_OK) return rc;
+        if (e->h_ctr->active == 0) break;
+    }
+    return CK_OK;
+}
+
+int ck_tree_root(ck_engine *e, uint32_t *n, float *w, int32_t *n_children) {
+    if (!e) return fail(CK_ERR_ARG, "ck_tree_root: null engine");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    Slot s;
+    int rc = manual_slot(e, &s);
+    if (rc != CK_OK) return rc;
+    uint4 st;
+    CK_CUDA(cudaMemcpy(&st, d.stat + (size_t)s.buf[s.cur] * d.cap + s.root[s.cur], sizeof(st), cudaMemcpyDeviceToHost));
+    if (n) *n = st.x;
+    if (w) memcpy(w, &st.y, 4);
+    if (n_children) *n_children = (int32_t)((st.w >> 22) & 63u);
+    return CK_OK;
+}
+
+int ck_tree_root_children(ck_engine *e, ck_pos *pos, uint32_t *n, float *w, float *p, int32_t *status) {
+    if (!e) return fail(CK_ERR_ARG, "ck_tree_root_children: null engine");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    Slot s;
+    int rc = manual_slot(e, &s);
+    if (rc != CK_OK) return rc;
+    const size_t base = (size_t)s.buf[s.cur] * d.cap;
+    uint4 st;
+    CK_CUDA(cudaMemcpy(&st, d.stat + base + s.root[s.cur], sizeof(st), cudaMemcpyDeviceToHost));
+    const int b = (int)((st.w >> 22) & 63u), fc = (int)(st.w & kFcMask);
+    if (b == 0) return CK_OK;
+    uint4 cs[CK_MAX_CHILDREN], cp[CK_MAX_CHILDREN];
+    CK_CUDA(cudaMemcpy(cs, d.stat + base + fc, b * sizeof(uint4), cudaMemcpyDeviceToHost));
+    CK_CUDA(cudaMemcpy(cp, d.pos + base + fc, b * sizeof(uint4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < b; ++i) {
+        if (pos) { pos[i].p1 = cp[i].x; pos[i].p2 = cp[i].y; pos[i].k = cp[i].z; pos[i].meta = cp[i].w; }
+        if (n) n[i] = cs[i].x;
+        if (w) memcpy(w + i, &cs[i].y, 4);
+        if (p) memcpy(p + i, &cs[i].z, 4);
+        if (status) status[i] = (int32_t)((cs[i].w >> 28) & 3u);
+    }
+    return CK_OK;
+}
+
+int ck_tree_best_child(ck_engine *e, int32_t move_count, int32_t *index) {
+    if (!e || !index) return fail(CK_ERR_ARG, "ck_tree_best_child: bad arguments");
+    (void)move_count;                      // temperature sampling is the engine's business; the shim asks for the robust child
+    uint32_t n[CK_MAX_CHILDREN];
+    int32_t b = 0;
+    int rc = ck_tree_root(e, nullptr, nullptr, &b);
+    if (rc != CK_OK) return rc;
+    if (b == 0) return fail(CK_ERR_STATE, "ck_tree_best_child: root has no children");
+    rc = ck_tree_root_children(e, nullptr, n, nullptr, nullptr, nullptr);
+    if (rc != CK_OK) return rc;
+    int best = 0;
+    for (int i = 1; i < b; ++i) if (n[i] > n[best]) best = i;     // np.argmax: first maximum (MCTS.py:236-238)
+    *index = best;
+    return CK_OK;
+}
+
+int ck_tree_advance(ck_engine *e, int32_t child_index) {
+    if (!e) return fail(CK_ERR_ARG, "ck_tree_advance: null engine");
+    EngineDev &d = e->dev;
+    DeviceGuard g(d.cfg.device);
+    Slot s;
+    int rc = manual_slot(e, &s);
+    if (rc != CK_OK) return rc;
+    const size_t base = (size_t)s.buf[s.cur] * d.cap;
+    uint4 st;
+    CK_CUDA(cudaMemcpy(&st, d.stat + base + s.root[s.cur], sizeof(st), cudaMemcpyDeviceToHost));
+    const int b = (int)((st.w >> 22) & 63u), fc = (int)(st.w & kFcMask);
+    if (child_index < 0 || child_index >= b) return fail(CK_ERR_ARG, "ck_tree_advance: child index out of range");
+    // MCTS.new_root_node for a one-ply advance (MCTS.py:281-288): the chosen child becomes the
+    // root of the same tree and keeps its statistics; its link already names its parent's player.
+    s.root[s.cur] = fc + child_index;
+    s.phase = PH_HALT; s.sims_done = 0;
+    CK_CUDA(cudaMemcpy(d.slots, &s, sizeof(Slot), cudaMemcpyHostToDevice));
+    return CK_OK;
+}
+
+int64_t ck_tree_node_count(ck_engine *e) {
+    if (!e) return -1;
+    DeviceGuard g(e->dev.cfg.device);
+    Slot s;
+    if (manual_slot(e, &s) != CK_OK) return -1;
+    return s.alloc[s.cur];
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+// ck_net.cu -- K3 policy/value network: weight handling, fp32 CUDA-core tower (cross-check
+// implementation), heads kernel (shared with the tcgen05 tower), C ABI.
+//
+// Architecture = create_nn (reference training_pipeline.py:44-120): 7 x [Conv3x3(128) -> ReLU
+// -> BN], policy head Conv3x3(128)->ReLU->BN->Conv1x1(8)->ReLU->BN->Flatten(x,y,c)->
+// Dense(512, softmax); value head Conv1x1(1)->ReLU->BN->Flatten->Dense(64, ReLU)->BN->
+// Dense(1, tanh).  Input planes per Checkers.py:37-48.
+#include <math.h>
+#include <vector>
+#include "ck_net.cuh"
+
+namespace ck {
+
+NetLayout net_layout() {
+    NetLayout L;
+    int64_t o = 0;
+    auto conv = [&](ConvParams &c, int k, int cin, int cout, bool bn) {
+        c.cin = cin; c.cout = cout;
+        c.kernel = o; o += (int64_t)k * k * cin * cout;
+        c.bias = o; o += cout;
+        if (bn) { c.gamma = o; o += cout; c.beta = o; o += cout; c.mean = o; o += cout; c.var = o; o += cout; }
+    };
+    conv(L.conv[0], 3, 14, kC, true);
+    for (int i = 1; i < 8; ++i) conv(L.conv[i], 3, kC, kC, true);
+    conv(L.pol1x1, 1, kC, 8, true);
+    L.pol_dense_k = o; o += 512 * 512; L.pol_dense_b = o; o += 512;
+    conv(L.val1x1, 1, kC, 1, true);
+    L.val_d1_k = o; o += 64 * 64; L.val_d1_b = o; o += 64;
+    L.val_d1_gamma = o; o += 64; L.val_d1_beta = o; o += 64; L.val_d1_mean = o; o += 64; L.val_d1_var = o; o += 64;
+    L.val_d2_k = o; o += 64; L.val_d2_b = o; o += 1;
+    L.total = o;
+    return L;
+}
+
+__constant__ float c_plane5[81];     // float32(n / 80.0) as numpy produces it (Checkers.py:346-361 + :432)
+static bool g_plane5_ready[64] = {false};
+
+static int ensure_constants(int device) {
+    if (device < 64 && g_plane5_ready[device]) return CK_OK;
+    float t[81];
+    for (int i = 0; i <= 80; ++i) t[i] = (float)((double)i / 80.0);
+    CK_CUDA(cudaMemcpyToSymbol(c_plane5, t, sizeof(t)));
+    if (device < 64) g_plane5_ready[device] = true;
+    return CK_OK;
+}
+
+// ---- folded batch-norm table ------------------------------------------------------------
+struct FoldJob { int64_t gamma, beta, mean, var; int n; int dst; };
+__global__ void fold_bn_kernel(const float *__restrict__ blob, float *__restrict__ out, FoldJob j) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= j.n) return;
+    const float sc = __fdiv_rn(blob[j.gamma + i], __fsqrt_rn(__fadd_rn(blob[j.var + i], kBnEps)));
+    out[j.dst + i] = sc;
+    out[j.dst + j.n + i] = __fsub_rn(blob[j.beta + i], __fmul_rn(blob[j.mean + i], sc));
+}
+
+// ---- network input ------------------------------------------------------------------------
+__device__ __forceinline__ float leaf_plane(const ck_leaf &L, int ci, int x, int y) {
+    if (ci == 4) return (float)(L.info & 1u);
+    if (ci == 5) return c_plane5[(L.info >> 8) & 0xFFu];
+    if (((x ^ y) & 1) == 0) return 0.f;
+    const uint32_t bit = 1u << (4 * x + (y >> 1));
+    uint32_t set;
+    switch (ci) {
+        case 0: set = L.p1 & ~L.k; break;
+        case 1: set = L.p1 & L.k; break;
+        case 2: set = L.p2 & ~L.k; break;
+        case 3: set = L.p2 & L.k; break;
+        default: set = L.mask[ci - 6]; break;
+    }
+    return (set & bit) ? 1.f : 0.f;
+}
+
+__global__ void planes_to_leaf_kernel(const float *__restrict__ x, int64_t n, ck_leaf *__restrict__ out) {
+    // inverse of leaf_plane for the Keras-signature entry point: x is [n,8,8,14] channels-last
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = x + i * 896;
+    uint32_t b[14];
+    for (int c = 0; c < 14; ++c) b[c] = 0;
+    for (int s = 0; s < 32; ++s) {
+        const int xx = s >> 2, yy = ((s & 3) << 1) | ((xx & 1) ^ 1);
+        for (int c = 0; c < 14; ++c)
+            if (c != 4 && c != 5 && p[(xx * 8 + yy) * 14 + c] != 0.f) b[c] |= 1u << s;
+    }
+    ck_leaf L;
+    L.p1 = b[0] | b[1]; L.p2 = b[2] | b[3]; L.k = b[1] | b[3];
+    const int player = p[4] != 0.f;
+    const int p5 = (int)lrintf(p[5] * 80.f);
+    L.info = (uint32_t)player | ((uint32_t)p5 << 8);
+    for (int c = 0; c < 8; ++c) L.mask[c] = b[6 + c];
+    out[i] = L;
+}
+
+// ---- fp32 CUDA-core tower (cross-check implementation) -------------------------------------
+// One CTA per position; thread = (output channel, half board); the padded input planes sit
+// in shared memory and are read as warp-wide broadcasts; weights stream from L2 in the
+// Keras [kh,kw,Cin,Cout] layout, coalesced over Cout.
+constexpr int kRowStride = 12;                 // padded row of 10 floats, 16-byte aligned
+constexpr int kPlaneStride = 10 * kRowStride;  // 10 padded rows
+
+template <int CIN, bool FROM_LEAF>
+__global__ void __launch_bounds__(256)
+conv3x3_simt_kernel(const ck_leaf *__restrict__ leaves, const float *__restrict__ in, const int32_t *__restrict__ n_dev,
+                    const float *__restrict__ w, const float *__restrict__ bias, const float *__restrict__ scale,
+                    float *__restrict__ out) {
+    const int pos = blockIdx.x;
+    if (n_dev != nullptr && pos >= *n_dev) return;
+    extern __shared__ __align__(16) float s_in[];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CIN * kPlaneStride; i += 256) s_in[i] = 0.f;
+    __syncthreads();
+    if (FROM_LEAF) {
+        const ck_leaf L = leaves[pos];
+        for (int i = tid; i < CIN * 64; i += 256) {
+            const int ci = i >> 6, x = (i >> 3) & 7, y = i & 7;
+            s_in[ci * kPlaneStride + (x + 1) * kRowStride + (y + 1)] = leaf_plane(L, ci, x, y);
+        }
+    } else {
+        const float *src = in + (int64_t)pos * CIN * 64;
+        for (int i = tid; i < CIN * 64; i += 256) {
+            const int ci = i >> 6, x = (i >> 3) & 7, y = i & 7;
+            s_in[ci * kPlaneStride + (x + 1) * kRowStride + (y + 1)] = src[i];
+        }
+    }
+    __syncthreads();
+    const int co = tid & 127, half = tid >> 7;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int ci = 0; ci < CIN; ++ci) {
+        float wk[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wk[t] = __ldg(w + ((int64_t)t * CIN + ci) * kC + co);
+        const float *ip = s_in + ci * kPlaneStride + (4 * half) * kRowStride;
+#pragma unroll
+        for (int r6 = 0; r6 < 6; ++r6) {
+            float v[12];
+            const float4 a = *reinterpret_cast<const float4 *>(ip + r6 * kRowStride);
+            const float4 b = *reinterpret_cast<const float4 *>(ip + r6 * kRowStride + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(ip + r6 * kRowStride + 8);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int r = r6 - kh;
+                if (r < 0 || r > 3) continue;
+#pragma unroll
+                for (int cx = 0; cx < 8; ++cx)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) acc[r * 8 + cx] = fmaf(v[cx + kw], wk[kh * 3 + kw], acc[r * 8 + cx]);
+            }
+        }
+    }
+    const float b = bias[co], sc = scale[co], sh = scale[kC + co];
+    float *dst = out + ((int64_t)pos * kC + co) * 64 + half * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        float4 o;
+        o.x = fmaf(fmaxf(acc[i] + b, 0.f), sc, sh);
+        o.y = fmaf(fmaxf(acc[i + 1] + b, 0.f), sc, sh);
+        o.z = fmaf(fmaxf(acc[i + 2] + b, 0.f), sc, sh);
+        o.w = fmaf(fmaxf(acc[i + 3] + b, 0.f), sc, sh);
+        *reinterpret_cast<float4 *>(dst + i) = o;
+    }
+}
+
+// ---- heads --------------------------------------------------------------------------------
+// 8 positions per CTA so that the 1 MB policy-dense matrix is read from L2 once per 8
+// positions.  Inputs: trunk = conv6 output, pconv = policy conv3x3 output, fp32 [n][128][64].
+constexpr int kHeadPB = 8;
+
+struct HeadParams {
+    int64_t pol1x1_k, pol1x1_b, pol_dense_k, pol_dense_b;
+    int64_t val1x1_k, val1x1_b, val_d1_k, val_d1_b, val_d2_k, val_d2_b;
+};
+
+__global__ void __launch_bounds__(256)
+heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, int64_t max_n,
+             const int32_t *__restrict__ n_dev, const float *__restrict__ blob, const float *__restrict__ fold,
+             HeadParams hp, float *__restrict__ policy, float *__restrict__ value) {
+    int64_t n = max_n;
+    if (n_dev != nullptr) n = min((int64_t)*n_dev, max_n);
+    const int64_t base = (int64_t)blockIdx.x * kHeadPB;
+    if (base >= n) return;
+    const int npos = (int)min((int64_t)kHeadPB, n - base);
+    __shared__ __align__(16) float s_flat[512 * kHeadPB];   // [i][p] during the dense, [p][512] for softmax
+    __shared__ float s_wp[128 * 8];
+    __shared__ float s_v1[kHeadPB][64];
+    __shared__ float s_h[kHeadPB][64];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    for (int i = tid; i < 128 * 8; i += 256) s_wp[i] = blob[hp.pol1x1_k + i];
+    __syncthreads();
+    // policy conv1x1 128 -> 8, ReLU, BN; flatten in (x, y, c) order
+    {
+        const int p = wp;
+        float acc[2][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[h][o] = 0.f;
+        if (p < npos) {
+            const float *src = pconv + (base + p) * kC * 64;
+            for (int c = 0; c < kC; ++c) {
+                const float a0 = src[c * 64 + lane], a1 = src[c * 64 + 32 + lane];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const float wv = s_wp[c * 8 + o];
+                    acc[0][o] = fmaf(a0, wv, acc[0][o]);
+                    acc[1][o] = fmaf(a1, wv, acc[1][o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const float v = fmaf(fmaxf(acc[h][o] + blob[hp.pol1x1_b + o], 0.f), fold[kScalePol1x1 + o], fold[kScalePol1x1 + 8 + o]);
+                s_flat[((h * 32 + lane) * 8 + o) * kHeadPB + p] = (p < npos) ? v : 0.f;
+            }
+    }
+    __syncthreads();
+    // policy dense 512 -> 512 (Keras kernel [in, out]): thread owns outputs tid and tid+256
+    float l0[kHeadPB], l1[kHeadPB];
+#pragma unroll
+    for (int p = 0; p < kHeadPB; ++p) { l0[p] = 0.f; l1[p] = 0.f; }
+    {
+        const float *wd = blob + hp.pol_dense_k;
+#pragma unroll 4
+        for (int i = 0; i < 512; ++i) {
+            const float w0 = __ldg(wd + i * 512 + tid), w1 = __ldg(wd + i * 512 + 256 + tid);
+            const float4 fa = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadPB]);
+            const float4 fb = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadPB + 4]);
+            const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+            for (int p = 0; p < kHeadPB; ++p) { l0[p] = fmaf(f[p], w0, l0[p]); l1[p] = fmaf(f[p], w1, l1[p]); }
+        }
+    }
+    __syncthreads();
+    {
+        const float b0 = blob[hp.pol_dense_b + tid], b1 = blob[hp.pol_dense_b + 256 + tid];
+#pragma unroll
+        for (int p = 0; p < kHeadPB; ++p) {
+            s_flat[p * 512 + tid] = l0[p] + b0;
+            s_flat[p * 512 + 256 + tid] = l1[p] + b1;
+        }
+    }
+    __syncthreads();
+    // softmax, one warp per position
+    if (wp < npos) {
+        float *row = s_flat + wp * 512;
+        float m = -INFINITY;
+        for (int i = lane; i < 512; i += 32) m = fmaxf(m, row[i]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        float e[16], s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { e[i] = expf(row[lane + 32 * i] - m); s += e[i]; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        float *dst = policy + (base + wp) * CK_POLICY_SIZE;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[lane + 32 * i] = e[i] / s;
+    }
+    // value head: conv1x1 128 -> 1, ReLU, BN
+    {
+        const int p = wp;
+        if (p < npos) {
+            const float *src = trunk + (base + p) * kC * 64;
+            float a0 = 0.f, a1 = 0.f;
+            for (int c = 0; c < kC; ++c) {
+                const float wv = blob[hp.val1x1_k + c];
+                a0 = fmaf(src[c * 64 + lane], wv, a0);
+                a1 = fmaf(src[c * 64 + 32 + lane], wv, a1);
+            }
+            const float b = blob[hp.val1x1_b], sc = fold[kScaleVal1x1], sh = fold[kScaleVal1x1 + 1];
+            s_v1[p][lane] = fmaf(fmaxf(a0 + b, 0.f), sc, sh);
+            s_v1[p][lane + 32] = fmaf(fmaxf(a1 + b, 0.f), sc, sh);
+        }
+    }
+    __syncwarp();
+    {
+        const int p = wp;
+        if (p < npos) {
+            // dense 64 -> 64, ReLU, BN
+            float h0 = 0.f, h1 = 0.f;
+            for (int s = 0; s < 64; ++s) {
+                const float v = s_v1[p][s];
+                h0 = fmaf(v, blob[hp.val_d1_k + s * 64 + lane], h0);
+                h1 = fmaf(v, blob[hp.val_d1_k + s * 64 + 32 + lane], h1);
+            }
+            h0 = fmaf(fmaxf(h0 + blob[hp.val_d1_b + lane], 0.f), fold[kScaleValD1 + lane], fold[kScaleValD1 + 64 + lane]);
+            h1 = fmaf(fmaxf(h1 + blob[hp.val_d1_b + 32 + lane], 0.f), fold[kScaleValD1 + 32 + lane], fold[kScaleValD1 + 96 + lane]);
+            // dense 64 -> 1, tanh
+            float t = h0 * blob[hp.val_d2_k + lane] + h1 * blob[hp.val_d2_k + 32 + lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            if (lane == 0) value[base + p] = tanhf(t + blob[hp.val_d2_b]);
+        }
+    }
+    (void)s_h;
+}
+
+// ---- host side -----------------------------------------------------------------------------
+int net_reserve(ck_net *net, int64_t n) {
+    if (n <= net->cap) return CK_OK;
+    cudaFree(net->d_act0); cudaFree(net->d_act1);
+    net->d_act0 = net->d_act1 = nullptr; net->cap = 0;
+    CK_CUDA(cudaMalloc(&net->d_act0, (size_t)n * kC * 64 * sizeof(float)));
+    CK_CUDA(cudaMalloc(&net->d_act1, (size_t)n * kC * 64 * sizeof(float)));
+    net->cap = n;
+    return CK_OK;
+}
+
+static int net_reserve_io(ck_net *net, int64_t n) {
+    if (n <= net->io_cap) return CK_OK;
+    cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value);
+    net->d_leaves = nullptr; net->d_policy = nullptr; net->d_value = nullptr; net->io_cap = 0;
+    CK_CUDA(cudaMalloc(&net->d_leaves, (size_t)n * sizeof(ck_leaf)));
+    CK_CUDA(cudaMalloc(&net->d_policy, (size_t)n * CK_POLICY_SIZE * sizeof(float)));
+    CK_CUDA(cudaMalloc(&net->d_value, (size_t)n * sizeof(float)));
+    net->io_cap = n;
+    return CK_OK;
+}
+
+static int net_finish_weights(ck_net *net) {
+    const NetLayout L = net_layout();
+    if (!net->d_scale) CK_CUDA(cudaMalloc(&net->d_scale, kScaleTotal * sizeof(float)));
+    std::vector<FoldJob> jobs;
+    for (int i = 0; i < 8; ++i) jobs.push_back({L.conv[i].gamma, L.conv[i].beta, L.conv[i].mean, L.conv[i].var, kC, kScaleTower + i * 2 * kC});
+    jobs.push_back({L.pol1x1.gamma, L.pol1x1.beta, L.pol1x1.mean, L.pol1x1.var, 8, kScalePol1x1});
+    jobs.push_back({L.val1x1.gamma, L.val1x1.beta, L.val1x1.mean, L.val1x1.var, 1, kScaleVal1x1});
+    jobs.push_back({L.val_d1_gamma, L.val_d1_beta, L.val_d1_mean, L.val_d1_var, 64, kScaleValD1});
+    for (const FoldJob &j : jobs) fold_bn_kernel<<<1, 128>>>(net->d_blob, net->d_scale, j);
+    CK_CUDA(cudaGetLastError());
+    int rc = net_tc_prepare(net);
+    if (rc != CK_OK) return rc;
+    CK_CUDA(cudaDeviceSynchronize());
+    net->have_weights = true;
+    return CK_OK;
+}
+
+int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
+                     float *d_policy, float *d_value, cudaStream_t stream, int *launches) {
+    if (!net->have_weights) return fail(CK_ERR_NO_NET, "ck_net: weights were never set");
+    if (max_n <= 0) return CK_OK;
+    int rc = net_reserve(net, max_n);
+    if (rc != CK_OK) return rc;
+    rc = ensure_constants(net->device);
+    if (rc != CK_OK) return rc;
+    const NetLayout L = net_layout();
+    const float *blob = net->d_blob;
+    float *trunk = net->d_act0, *pconv = net->d_act1;
+    int nl = 0;
+    if (net->impl == CK_NET_IMPL_SIMT) {
+        static bool attr_done = false;
+        const int smem128 = kC * kPlaneStride * sizeof(float), smem14 = 14 * kPlaneStride * sizeof(float);
+        if (!attr_done) {
+            CK_CUDA(cudaFuncSetAttribute(conv3x3_simt_kernel<kC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));
+            attr_done = true;
+        }
+        float *a = net->d_act0, *b = net->d_act1;
+        conv3x3_simt_kernel<14, true><<<(unsigned)max_n, 256, smem14, stream>>>(
+            d_leaves, nullptr, n_dev, blob + L.conv[0].kernel, blob + L.conv[0].bias, net->d_scale + kScaleTower, a);
+        ++nl;
+        for (int i = 1; i < 8; ++i) {
+            conv3x3_simt_kernel<kC, false><<<(unsigned)max_n, 256, smem128, stream>>>(
+                nullptr, a, n_dev, blob + L.conv[i].kernel, blob + L.conv[i].bias, net->d_scale + kScaleTower + i * 2 * kC, b);
+            ++nl;
+            if (i < 7) { float *t = a; a = b; b = t; }   // after conv6 keep a = trunk, b = policy conv output
+        }
+        trunk = a; pconv = b;
+        CK_CUDA(cudaGetLastError());
+    } else {
+        rc = net_tc_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl);
+        if (rc != CK_OK) return rc;
+    }
+    HeadParams hp{L.pol1x1.kernel, L.pol1x1.bias, L.pol_dense_k, L.pol_dense_b, L.val1x1.kernel, L.val1x1.bias,
+                  L.val_d1_k, L.val_d1_b, L.val_d2_k, L.val_d2_b};
+    heads_kernel<<<(unsigned)((max_n + kHeadPB - 1) / kHeadPB), 256, 0, stream>>>(
+        trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
+    ++nl;
+    CK_CUDA(cudaGetLastError());
+    if (launches) *launches += nl;
+    return CK_OK;
+}
+
+}  // namespace ck
+
+using namespace ck;
+
+extern "C" {
+
+ck_net *ck_net_create(int device) {
+    DeviceGuard g(device);
+    if (!g.ok) { fail(CK_ERR_CUDA, "ck_net_create: cannot select CUDA device " + std::to_string(device)); return nullptr; }
+    ck_net *net = new ck_net();
+    net->device = device;
+    CK_CUDA_PTR(cudaMalloc(&net->d_blob, CK_NET_PARAM_COUNT * sizeof(float)));
+    return net;
+}
+
+void ck_net_destroy(ck_net *net) {
+    if (!net) return;
+    DeviceGuard g(net->device);
+    cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack);
+    cudaFree(net->d_act0); cudaFree(net->d_act1);
+    cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value);
+    delete net;
+}
+
+int ck_net_set_impl(ck_net *net, int impl) {
+    if (!net || (impl != CK_NET_IMPL_TC && impl != CK_NET_IMPL_SIMT)) return fail(CK_ERR_ARG, "ck_net_set_impl: bad arguments");
+    net->impl = impl;
+    return CK_OK;
+}
+
+int ck_net_set_weights(ck_net *net, const float *blob, int64_t count) {
+    if (!net || !blob || count != net_layout().total || count != CK_NET_PARAM_COUNT)
+        return fail(CK_ERR_ARG, "ck_net_set_weights: expected " + std::to_string(CK_NET_PARAM_COUNT) + " floats");
+    DeviceGuard g(net->device);
+    CK_CUDA(cudaMemcpy(net->d_blob, blob, count * sizeof(float), cudaMemcpyHostToDevice));
+    return net_finish_weights(net);
+}
+
+int ck_net_set_weights_device(ck_net *net, const float *d_blob, int64_t count) {
+    if (!net || !d_blob || count != CK_NET_PARAM_COUNT)
+        return fail(CK_ERR_ARG, "ck_net_set_weights_device: expected " + std::to_string(CK_NET_PARAM_COUNT) + " floats");
+    DeviceGuard g(net->device);
+    CK_CUDA(cudaMemcpy(net->d_blob, d_blob, count * sizeof(float), cudaMemcpyDeviceToDevice));
+    return net_finish_weights(net);
+}
+
+int ck_net_forward_device(ck_net *net, const ck_leaf *d_leaves, int64_t n, float *d_policy, float *d_value, void *stream) {
+    if (!net || n < 0) return fail(CK_ERR_ARG, "ck_net_forward_device: bad arguments");
+    DeviceGuard g(net->device);
+    return net_forward_rows(net, d_leaves, n, nullptr, d_policy, d_value, (cudaStream_t)stream, nullptr);
+}
+
+int ck_net_forward(ck_net *net, const ck_leaf *leaves, int64_t n, float *policy, float *value) {
+    if (!net || !leaves || n < 0) return fail(CK_ERR_ARG, "ck_net_forward: bad arguments");
+    if (n == 0) return CK_OK;
+    DeviceGuard g(net->device);
+    int rc = net_reserve_io(net, n);
+    if (rc != CK_OK) return rc;
+    CK_CUDA(cudaMemcpy(net->d_leaves, leaves, n * sizeof(ck_leaf), cudaMemcpyHostToDevice));
+    rc = net_forward_rows(net, net->d_leaves, n, nullptr, net->d_policy, net->d_value, nullptr, nullptr);
+    if (rc != CK_OK) return rc;
+    CK_CUDA(cudaDeviceSynchronize());
+    if (policy) CK_CUDA(cudaMemcpy(policy, net->d_policy, n * CK_POLICY_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
+    if (value) CK_CUDA(cudaMemcpy(value, net->d_value, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return CK_OK;
+}
+
+int ck_net_forward_planes(ck_net *net, const float *x, int64_t n, float *policy, float *value) {
+    if (!net || !x || n < 0) return fail(CK_ERR_ARG, "ck_net_forward_planes: bad arguments");
+    if (n == 0) return CK_OK;
+    DeviceGuard g(net->device);
+    int rc = net_reserve_io(net, n);
+    if (rc != CK_OK) return rc;
+    float *d_x = nullptr;
+    CK_CUDA(cudaMalloc(&d_x, n * 896 * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d_x, x, n * 896 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        planes_to_leaf_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d_x, n, net->d_leaves);
+        e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_x);
+    if (e != cudaSuccess) return fail(CK_ERR_CUDA, std::string("ck_net_forward_planes: ") + cudaGetErrorString(e));
+    rc = net_forward_rows(net, net->d_leaves, n, nullptr, net->d_policy, net->d_value, nullptr, nullptr);
+    if (rc != CK_OK) return rc;
+    CK_CUDA(cudaDeviceSynchronize());
+    if (policy) CK_CUDA(cudaMemcpy(policy, net->d_policy, n * CK_POLICY_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
+    if (value) CK_CUDA(cudaMemcpy(value, net->d_value, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return CK_OK;
+}
+
+}  // extern "C"

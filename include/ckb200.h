@@ -1,0 +1,205 @@
+/* ckb200.h -- C ABI of libckb200.so: B200-native batched Checkers self-play engine.
+ *
+ * The reference (AlexMGitHub/Checkers-MCTS) has no FFI layer; its seams are duck-typed
+ * Python objects.  Each entry point below names the reference code it
+ * replaces (file:line into the reference tree).  All pointers are plain host pointers
+ * unless the name ends in _device; no torch / CUDA types appear in any signature
+ * (streams are passed as void*).  Every function returns CK_OK (0) or a CK_ERR_* code;
+ * ck_last_error() gives the message of the last failure on the calling thread.
+ *
+ * There is no CPU fallback behind this ABI: every compute entry point runs CUDA
+ * kernels compiled for sm_100a and fails with CK_ERR_CUDA when no device is usable.
+ */
+#ifndef CKB200_H
+#define CKB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CK_ABI_VERSION 1
+#define CK_MAX_CHILDREN 48          /* 12 kings x 4 directions */
+#define CK_POLICY_SIZE 512          /* 8 action planes x 8 x 8 (Checkers.py:434) */
+#define CK_NET_PARAM_COUNT 1321774  /* create_nn, training_pipeline.py:44-120 */
+
+enum { CK_ONGOING = 0, CK_P1_WINS = 1, CK_P2_WINS = 2, CK_DRAW = 3 };
+enum {
+    CK_OK = 0, CK_ERR_CUDA = 1, CK_ERR_ARG = 2, CK_ERR_POOL_OVERFLOW = 3,
+    CK_ERR_DEPTH = 4, CK_ERR_STATE = 5, CK_ERR_NOMEM = 6, CK_ERR_NO_NET = 7
+};
+
+/* Compact position.  Square s = 4*x + (y>>1) over the playable squares x%2 != y%2
+ * (x = row, y = column, Checkers.py:415-423).  p1/p2: all pieces of each side; k: kings
+ * of either side.  meta: bit0 player to move (0 = player1), bits1-7 `rev` (consecutive
+ * reversible plies, saturating at 127), bits8-16 action id (plane-6)*64 + x*8 + y of the
+ * move that produced the position (Checkers.py:138-143), bit17 action valid,
+ * bits18-31 ply index (len(history)-1, saturating). */
+typedef struct { uint32_t p1, p2, k, meta; } ck_pos;
+
+/* Compact network input for one position: planes 0-4 from pos, plane 5 = plane5/80,
+ * planes 6-13 = mask (Checkers.py:37-48, 431-432). */
+typedef struct { uint32_t p1, p2, k, info /* bit0 player, bits8-15 plane5 numerator, bits16-31 game tag (stub evaluators only) */; uint32_t mask[8]; } ck_leaf;
+
+const char *ck_last_error(void);
+int ck_abi_version(void);
+int ck_device_count(void);
+
+/* ---- K1: legal successors + outcome -------------------------------------------------
+ * Replaces Checkers._check_moves/_check_jumps/_check_king_jumps (Checkers.py:94-304) and
+ * determine_outcome (:306-364) for a batch of n positions.  children[i*max_children + j]
+ * is the j-th entry of the reference's raw legal list (generation order); counts[i] the
+ * list length; masks[i*8 + p] plane 6+p as a 32-bit square set; status[i] CK_*;
+ * plane5[i] the numerator of state[5] (= n/80).  Any output pointer may be NULL. */
+int ck_movegen(int device, const ck_pos *pos, int64_t n, int32_t max_children,
+               ck_pos *children, int32_t *counts, uint32_t *masks, uint8_t *status, uint8_t *plane5);
+/* same on device buffers; launches on `stream` (cudaStream_t) and does not synchronise.
+ * elapsed_ms (optional, host) makes the call time itself with CUDA events on `stream`. */
+int ck_movegen_device(const ck_pos *d_pos, int64_t n, int32_t max_children, ck_pos *d_children,
+                      int32_t *d_counts, uint32_t *d_masks, uint8_t *d_status, uint8_t *d_plane5,
+                      void *stream);
+
+/* ---- K4: random playouts -----------------------------------------------------------
+ * MCTS.default_policy, non-NN branch (MCTS.py:132-143): uniformly random legal moves to
+ * the end of the game.  outcome[i] CK_*; plies[i] the playout length.  max_plies <= 0:
+ * unlimited. */
+int ck_rollout(int device, const ck_pos *pos, int64_t n, uint64_t seed, int32_t max_plies,
+               uint8_t *outcome, int32_t *plies);
+
+/* ---- K3: policy/value network ------------------------------------------------------
+ * Replaces neural_net.predict behind Checkers.predict (Checkers.py:425-438); the
+ * architecture is create_nn (training_pipeline.py:44-120).  Weights are one float32 blob
+ * of CK_NET_PARAM_COUNT values in Keras layer order and Keras layouts (conv kernels
+ * [kh,kw,Cin,Cout], dense [in,out], BN gamma,beta,moving_mean,moving_variance):
+ *   for L in conv0..conv6:      kernel, bias, gamma, beta, mean, var
+ *   policy conv3x3 (128->128):  kernel, bias, gamma, beta, mean, var
+ *   policy conv1x1 (128->8):    kernel, bias, gamma, beta, mean, var
+ *   policy dense (512->512):    kernel, bias
+ *   value conv1x1 (128->1):     kernel, bias, gamma, beta, mean, var
+ *   value dense (64->64):       kernel, bias, gamma, beta, mean, var
+ *   value dense (64->1):        kernel, bias
+ */
+typedef struct ck_net ck_net;
+enum { CK_NET_IMPL_TC = 0 /* tcgen05 split-fp16 tower */, CK_NET_IMPL_SIMT = 1 /* fp32 CUDA-core cross-check */ };
+ck_net *ck_net_create(int device);
+void ck_net_destroy(ck_net *);
+int ck_net_set_impl(ck_net *, int impl);
+int ck_net_set_weights(ck_net *, const float *blob, int64_t count);          /* host blob */
+int ck_net_set_weights_device(ck_net *, const float *d_blob, int64_t count); /* device blob (e.g. a torch tensor) */
+/* raw softmax policy [n,512] and tanh value [n] (what Keras predict returns) */
+int ck_net_forward(ck_net *, const ck_leaf *leaves, int64_t n, float *policy, float *value);
+/* Keras signature: x float32 [n,8,8,14] channels-last (Checkers.py:431-433) */
+int ck_net_forward_planes(ck_net *, const float *x, int64_t n, float *policy, float *value);
+int ck_net_forward_device(ck_net *, const ck_leaf *d_leaves, int64_t n, float *d_policy, float *d_value,
+                          void *stream);
+/* Checkers.predict glue (Checkers.py:434-437): prior = policy*mask / sum(policy*mask) with
+ * numpy's float32 pairwise summation order; masks[i*8+p]; bit-exact. */
+int ck_mask_renorm(int device, const float *policy, const uint32_t *masks, int64_t n, float *prior);
+
+/* ---- engine: self-play / arena (K2, K5, K6) -----------------------------------------
+ * Replaces MCTS.tree_policy/select_child/backpropagation/begin_tree_search/best_child/
+ * new_root_node (MCTS.py:59-295, 350-430) and the game loops
+ * generate_Checkers_data._generate_data (training_pipeline.py:334-419) and
+ * tournament_Checkers._start_tournament (:505-559). */
+enum { CK_EVAL_NET = 0, CK_EVAL_UNIFORM_ZERO = 1, CK_EVAL_UNIFORM_MATERIAL = 2, CK_EVAL_HASH = 3,
+       CK_EVAL_HASH_SALTED = 4 /* hash stub salted with the global game id: concurrent games differ */ };
+
+typedef struct {
+    int32_t device;
+    int32_t n_slots;          /* concurrent games resident on the GPU */
+    int32_t pool_cap;         /* nodes per tree buffer (0: default) */
+    int32_t max_plies;        /* history capacity per game (0: default 2048) */
+    int32_t budget;           /* BUDGET, CONSTRAINT='rollout' (MCTS.py:188-201) */
+    int32_t training;         /* TRAINING */
+    int32_t tau_decay_delay;  /* TEMP_DECAY_DELAY */
+    int32_t terminate_cnt;    /* TERMINATE_CNT; <= 0: no ply cap (tournament) */
+    double uct_c;             /* UCT_C */
+    double alpha, epsilon;    /* DIRICHLET_ALPHA / DIRICHLET_EPSILON */
+    double tau, tau_decay;    /* TEMPERATURE_TAU / TEMPERATURE_DECAY */
+    uint64_t seed;
+    int32_t evaluator;        /* CK_EVAL_* ; stubs exist for deterministic parity tests */
+    int32_t evaluator_p2;     /* arena with stub evaluators: evaluator of the second net; -1: same */
+    int32_t arena;            /* 0 self-play (one net); 1 arena: net 0 is player1 in games < n/2 (:523-528) */
+    int32_t keep_records;     /* store training records (self-play) */
+    int32_t reference_tau_quirk; /* 1: tau is never reset between games */
+    int32_t game_id_base;     /* global id of local game i = base + i*stride (multi-GPU sharding) */
+    int32_t game_id_stride;   /* 0 is treated as 1 */
+    int32_t max_terminal_sims_per_step; /* 0: default 64 */
+    int32_t compact_always;   /* 1: compact the kept subtree at every re-root (default: only when the pool runs low) */
+    int32_t reserved0;
+} ck_engine_cfg;
+
+typedef struct {
+    ck_pos   pos;             /* root state (training_pipeline.py:369) */
+    uint32_t mask[8];         /* planes 6..13 */
+    int32_t  plane5;          /* numerator of plane 5 */
+    int32_t  n_children;      /* 0 for the terminal record (:406-409) */
+    uint16_t action[CK_MAX_CHILDREN];  /* child action ids in node.children order */
+    uint32_t visits[CK_MAX_CHILDREN];  /* child.n (prob = n / sum n, :433-434) */
+    float    q;               /* root q from the root player's view (:365-368) */
+    int32_t  z;               /* _add_rewards (:439-455) */
+    uint32_t root_n;
+    float    root_w;
+    int32_t  chosen;          /* chosen action id, -1 for the terminal record */
+    int32_t  game;            /* global game id */
+    int32_t  ply;             /* index of the record inside its game */
+} ck_record;
+
+typedef struct {
+    int32_t game;             /* global game id */
+    int32_t outcome;          /* CK_* (adjudicated when terminated) */
+    int32_t move_count;
+    int32_t terminated;       /* hit TERMINATE_CNT */
+    int32_t n_records;
+    int32_t reroot_misses;    /* MCTS.py:292 would have raised */
+    int32_t p1_net;           /* arena: which net played player1 */
+    int32_t reserved;
+    uint64_t sims, nn_evals;
+} ck_game_result;
+
+typedef struct {
+    uint64_t sims;            /* root.selection() calls completed (MCTS.py:220,430) */
+    uint64_t nn_evals;        /* leaf evaluations */
+    uint64_t steps;           /* tree-step + eval rounds executed */
+    uint64_t games_finished;
+    uint64_t moves;
+    uint64_t nodes_created;
+    uint64_t compactions;
+    double   gpu_ms;          /* CUDA-event time of the call on the engine's stream */
+    double   eval_ms;         /* of which inside the evaluator (net) kernels; 0 if not measured */
+    uint64_t kernel_launches;
+} ck_run_stats;
+
+typedef struct ck_engine ck_engine;
+ck_engine *ck_engine_create(const ck_engine_cfg *cfg);
+void ck_engine_destroy(ck_engine *);
+int ck_engine_set_net(ck_engine *, int which /*0|1*/, ck_net *net);
+/* stage n_games new games (all from the start position); clears finished-game storage */
+int ck_engine_begin(ck_engine *, int64_t n_games);
+/* run at most n_steps lock-step rounds (n_steps <= 0: until every staged game finished) */
+int ck_engine_run(ck_engine *, int64_t n_steps, ck_run_stats *stats);
+/* convenience: begin + run to completion == _generate_data / _start_tournament */
+int ck_selfplay_run(ck_engine *, int64_t n_games, ck_run_stats *stats);
+int ck_arena_run(ck_engine *, int64_t n_games, ck_run_stats *stats);
+int64_t ck_games_finished(ck_engine *);
+int ck_games_fetch(ck_engine *, ck_game_result *out, int64_t cap);
+int64_t ck_records_count(ck_engine *);
+int ck_records_fetch(ck_engine *, ck_record *out, int64_t cap);
+/* time the evaluator separately inside ck_engine_run (adds two events per step) */
+int ck_engine_set_profile(ck_engine *, int on);
+
+/* ---- single-search API behind the MCTS / MCTS_Node shim (MCTS.py:210-295) ------------
+ * The engine must have been created with n_slots >= 1; these calls use slot 0 only. */
+int ck_tree_set_root(ck_engine *, const ck_pos *root, int32_t parent_player /* -1: opposite of root's */);
+int ck_tree_search(ck_engine *, int32_t sims);
+int ck_tree_root(ck_engine *, uint32_t *n, float *w, int32_t *n_children);
+int ck_tree_root_children(ck_engine *, ck_pos *pos, uint32_t *n, float *w, float *p, int32_t *status);
+int ck_tree_best_child(ck_engine *, int32_t move_count, int32_t *index);
+/* re-root on the child with this index (MCTS.new_root_node for a one-ply advance) */
+int ck_tree_advance(ck_engine *, int32_t child_index);
+int64_t ck_tree_node_count(ck_engine *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -318,9 +318,18 @@ static uint32_t mix32(uint32_t h) {
     return h;
 }
 
+static void eval_hash_impl(const cko_pos *pos, int plane5, float *policy, float *value, uint32_t salt);
 void cko_eval_hash(const cko_pos *pos, const uint32_t *mask, int plane5, float *policy, float *value, void *ctx) {
     (void)mask; (void)ctx;
-    uint32_t h = mix32(pos->p1 ^ 0x9e3779b9u);
+    eval_hash_impl(pos, plane5, policy, value, 0u);
+}
+/* ctx points at a uint32 salt (tests use the game id) so that concurrent games differ */
+void cko_eval_hash_salted(const cko_pos *pos, const uint32_t *mask, int plane5, float *policy, float *value, void *ctx) {
+    (void)mask;
+    eval_hash_impl(pos, plane5, policy, value, *(const uint32_t *)ctx);
+}
+static void eval_hash_impl(const cko_pos *pos, int plane5, float *policy, float *value, uint32_t salt) {
+    uint32_t h = mix32(pos->p1 ^ 0x9e3779b9u ^ (salt * 0x9E3779B1u));
     h = mix32(h ^ pos->p2);
     h = mix32(h ^ pos->k);
     h = mix32(h ^ (pos->meta & 1u) ^ ((uint32_t)plane5 << 8));

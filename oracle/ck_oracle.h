@@ -52,6 +52,8 @@ void cko_eval_uniform_material(const cko_pos *, const uint32_t *, int, float *, 
 /* deterministic pseudo-random peaky policy + value from an integer hash of the position;
  * exact float ops only so that the CUDA stub evaluator can reproduce it bit for bit */
 void cko_eval_hash(const cko_pos *, const uint32_t *, int, float *, float *, void *);
+/* same with the hash salted by *(uint32_t*)ctx (0 == cko_eval_hash) */
+void cko_eval_hash_salted(const cko_pos *, const uint32_t *, int, float *, float *, void *);
 
 typedef struct {
     double uct_c;        /* UCT_C */

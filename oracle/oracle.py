@@ -147,7 +147,7 @@ def make_cfg(uct_c=4.0, budget=400, training=False, alpha=1.0, epsilon=0.0, tau=
                float(tau), float(tau_decay), int(tau_decay_delay), int(terminate_cnt), int(seed))
 
 
-BUILTIN_EVALS = ("uniform_zero", "uniform_material", "hash")
+BUILTIN_EVALS = ("uniform_zero", "uniform_material", "hash", "hash_salted")
 
 
 def _resolve_eval(ev):
@@ -218,14 +218,17 @@ class Tree(object):
 
 
 class Game(object):
-    def __init__(self, cfg, eval_p1="uniform_zero", eval_p2=None):
+    def __init__(self, cfg, eval_p1="uniform_zero", eval_p2=None, salt=None):
+        """salt: uint32 handed to the evaluators as ctx (only 'hash_salted' reads it)."""
         self._f1, self._k1 = _resolve_eval(eval_p1)
         if eval_p2 is None:
             self._f2, self._k2 = None, None
         else:
             self._f2, self._k2 = _resolve_eval(eval_p2)
         self.cfg = cfg
-        self._h = lib().cko_game_new(C.byref(cfg), self._f1, None, self._f2, None)
+        self._salt = C.c_uint32(0 if salt is None else int(salt))
+        ctx = C.cast(C.pointer(self._salt), C.c_void_p)
+        self._h = lib().cko_game_new(C.byref(cfg), self._f1, ctx, self._f2, ctx)
 
     def play_ply(self):
         return bool(lib().cko_game_play_ply(self._h))

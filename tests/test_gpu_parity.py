@@ -1,0 +1,379 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ckb200.lib -> libckb200.so), against
+the CPU oracle on the same inputs and against the committed golden vectors (generated from the
+unmodified reference).  Integer / index work and the deterministic tree (epsilon = 0, tau = 0)
+are bit-exact; the network is checked within 1e-5 (north_star tolerance)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, codec, record_planes
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NET_TOL = 1e-5          # absolute, on softmax policy outputs and the tanh value
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ckb200 import lib as L
+    L.require_device()
+    return L
+
+
+def _pos_arr(L, positions):
+    a = np.zeros(len(positions), dtype=L.POS_DTYPE)
+    for i, p in enumerate(positions):
+        a[i] = tuple(int(v) for v in p)
+    return a
+
+
+def _check_movegen(L, positions):
+    out = L.movegen(_pos_arr(L, positions))
+    for i, p in enumerate(positions):
+        kids, mask, status, p5 = O.movegen(p)
+        assert out["counts"][i] == len(kids)
+        got = [tuple(int(v) for v in out["children"][i, j]) for j in range(len(kids))]
+        assert got == kids
+        assert [int(v) for v in out["masks"][i]] == mask
+        assert int(out["status"][i]) == status and int(out["plane5"][i]) == p5
+
+
+# ---- K1 -------------------------------------------------------------------------------------
+def test_movegen_golden(lib):
+    g = np.load(os.path.join(GOLDEN, "movegen_cases.npz"))
+    pos = g["pos"]
+    out = lib.movegen(_pos_arr(lib, pos))
+    off = np.concatenate([[0], np.cumsum(g["counts"])])
+    assert (out["counts"] == g["counts"]).all()
+    assert (out["masks"] == g["mask"]).all()
+    assert (out["status"] == g["status"]).all() and (out["plane5"] == g["plane5"]).all()
+    for i in range(len(pos)):
+        ref = g["kids"][off[i]:off[i + 1]]
+        ch = out["children"][i, :len(ref)]
+        assert (ch["p1"] == ref[:, 0]).all() and (ch["p2"] == ref[:, 1]).all() and (ch["k"] == ref[:, 2]).all()
+        assert ((ch["meta"] & 1) == ref[:, 3]).all() and (((ch["meta"] >> 8) & 0x1FF) == ref[:, 4]).all()
+
+
+def test_movegen_random_walks_vs_oracle(lib):
+    rng = np.random.RandomState(123)
+    positions = []
+    for _ in range(80):
+        pos = O.start_position()
+        for _ply in range(300):
+            positions.append(pos)
+            kids, _, st, _ = O.movegen(pos)
+            if st != codec.ONGOING:
+                break
+            pos = kids[rng.randint(len(kids))]
+    assert len(positions) > 4000
+    _check_movegen(lib, positions)
+
+
+def test_movegen_edge_cases(lib):
+    # empty batch, a side without pieces, a blocked side, maximum king mobility, late-ply draw window
+    assert len(lib.movegen(np.zeros(0, dtype=lib.POS_DTYPE))["counts"]) == 0
+    cases = [
+        (0x00000FFF, 0, 0, codec.make_meta(1)),
+        (0, 0xFFF00000, 0, codec.make_meta(0)),
+        (0x1, 0x30, 0, codec.make_meta(0)),
+        (0x0F0F0F00, 0x1, 0x0F0F0F01, codec.make_meta(0, 79, 0, 0, 120)),
+        (0x00000400, 0x00200000, 0x00200400, codec.make_meta(1, 78, 0, 0, 79)),
+        (0x00000400, 0x00200000, 0x00200400, codec.make_meta(1, 90, 0, 0, 300)),
+    ]
+    _check_movegen(lib, cases)
+    out = lib.movegen(_pos_arr(lib, cases[3:4]))
+    assert out["counts"][0] > 24       # twelve kings
+
+
+def test_movegen_large_batch_properties(lib):
+    """full-size sweep (2^20 positions): every position's outputs equal those of its duplicates and
+    the batch result does not depend on the batch it was computed in."""
+    rng = np.random.RandomState(5)
+    base = []
+    pos = O.start_position()
+    for _ in range(64):
+        base.append(pos)
+        kids, _, st, _ = O.movegen(pos)
+        if st != codec.ONGOING:
+            pos = O.start_position()
+        else:
+            pos = kids[rng.randint(len(kids))]
+    small = _pos_arr(lib, base)
+    ref = lib.movegen(small)
+    idx = rng.randint(0, len(base), size=1 << 20)
+    big = lib.movegen(small[idx], want_children=False)
+    assert (big["counts"] == ref["counts"][idx]).all()
+    assert (big["masks"] == ref["masks"][idx]).all()
+    assert (big["status"] == ref["status"][idx]).all()
+
+
+# ---- Checkers.predict glue -----------------------------------------------------------------
+def test_mask_renorm_golden(lib):
+    g = np.load(os.path.join(GOLDEN, "predict_glue.npz"))
+    out = lib.mask_renorm(g["policy"], g["mask"])
+    assert out.tobytes() == np.ascontiguousarray(g["prior"], dtype=np.float32).tobytes()
+
+
+# ---- K2: deterministic tree ------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["uniform_zero", "uniform_material", "hash"])
+def test_first_search_golden(lib, kind):
+    kat = json.load(open(os.path.join(GOLDEN, "mcts_kat.json")))[kind + "_first_search"]
+    eng = lib.Engine(lib.make_cfg(n_slots=1, budget=kat["budget"], evaluator=kind, keep_records=False))
+    eng.tree_set_root(O.start_position())
+    eng.tree_search(kat["budget"])
+    n, w, b = eng.tree_root()
+    assert n == kat["root_n"] and float(w) == kat["root_w"] and b == len(kat["children"])
+    for c, r in zip(eng.tree_root_children(), kat["children"]):
+        assert codec.meta_action(c["pos"][3]) == r["action"]
+        assert c["n"] == r["n"] and float(c["w"]) == r["w"] and float(c["p"]) == r["p"]
+    eng.close()
+
+
+def test_tree_api_advance_matches_oracle(lib):
+    """search, advance to the robust child, search again (tree reuse) == oracle tree."""
+    cfg = O.make_cfg(budget=150)
+    t = O.Tree(O.start_position(), cfg, "hash")
+    eng = lib.Engine(lib.make_cfg(n_slots=1, budget=150, evaluator="hash", keep_records=False))
+    eng.tree_set_root(O.start_position())
+    t.search(150)
+    eng.tree_search(150)
+    got, ref = eng.tree_root_children(), t.root_children()
+    assert [(c["n"], float(c["w"]), float(c["p"])) for c in got] == [(c["n"], float(c["w"]), float(c["p"])) for c in ref]
+    assert eng.tree_best_child() == t.best_child()
+    assert eng.tree_node_count() == t.node_count()
+    eng.close()
+
+
+def _engine_records(lib, eng):
+    recs = eng.records()
+    games = eng.games()
+    out = {}
+    for r in recs:
+        n = int(r["n_children"])
+        out.setdefault(int(r["game"]), []).append(dict(
+            pos=tuple(int(v) for v in r["pos"]), mask=[int(v) for v in r["mask"]], plane5=int(r["plane5"]),
+            actions=[int(v) for v in r["action"][:n]], visits=[int(v) for v in r["visits"][:n]],
+            q=np.float32(r["q"]), z=int(r["z"]), root_n=int(r["root_n"]), root_w=np.float32(r["root_w"]),
+            chosen=int(r["chosen"])))
+    return out, {int(g["game"]): g for g in games}
+
+
+def _same_record(a, b):
+    return (a["pos"] == b["pos"] and a["mask"] == b["mask"] and a["plane5"] == b["plane5"]
+            and a["actions"] == b["actions"] and a["visits"] == b["visits"]
+            and np.float32(a["q"]).tobytes() == np.float32(b["q"]).tobytes() and a["z"] == b["z"]
+            and a["root_n"] == b["root_n"] and np.float32(a["root_w"]).tobytes() == np.float32(b["root_w"]).tobytes()
+            and a["chosen"] == b["chosen"])
+
+
+@pytest.mark.parametrize("kind", ["uniform_zero", "uniform_material", "hash"])
+def test_game_opening_golden(lib, kind):
+    kat = json.load(open(os.path.join(GOLDEN, "mcts_kat.json")))[kind + "_game"]
+    eng = lib.Engine(lib.make_cfg(n_slots=1, budget=kat["budget"], training=True, terminate_cnt=kat["terminate_cnt"],
+                                  evaluator=kind))
+    eng.selfplay(1)
+    recs, _ = _engine_records(lib, eng)
+    recs = recs[0]
+    assert len(recs) == len(kat["moves"])
+    for r, m in zip(recs, kat["moves"]):
+        assert r["root_n"] == m["root_n"] and float(r["root_w"]) == m["root_w"]
+        assert r["actions"] == [c["action"] for c in m["children"]]
+        assert r["visits"] == [c["n"] for c in m["children"]]
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", ["hash", "uniform_material"])
+def test_selfplay_records_golden(lib, kind):
+    f = np.load(os.path.join(GOLDEN, "selfplay_%s.npz" % kind))
+    meta = json.loads(str(f["meta"]))
+    eng = lib.Engine(lib.make_cfg(n_slots=1, budget=meta["budget"], training=True,
+                                  terminate_cnt=meta["terminate_cnt"], evaluator=kind))
+    eng.selfplay(1)
+    recs, games = _engine_records(lib, eng)
+    recs = recs[0]
+    assert len(recs) == len(f["q"]) and games[0]["reroot_misses"] == 0
+    for i, r in enumerate(recs):
+        state, probs = record_planes(r)
+        pl = [codec.plane_to_bits(state[j]) for j in (0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13)]
+        assert pl == [int(v) for v in f["planes"][i]]
+        assert int(state[4, 0, 0]) == f["player"][i] and r["plane5"] == f["plane5"][i]
+        assert [int(v) for v in state[14, 0, 0:3]] == [int(v) for v in f["action"][i]]
+        assert probs.reshape(512).tobytes() == f["probs"][i].tobytes()
+        assert float(r["q"]) == f["q"][i] and r["z"] == f["z"][i]
+    eng.close()
+
+
+def test_tournament_golden(lib):
+    t = json.load(open(os.path.join(GOLDEN, "tournament.json")))
+    kinds = t["nets"]
+    rows = t["outcomes"]
+    first = rows[0]
+    eng = lib.Engine(lib.make_cfg(n_slots=2, budget=t["budget"], training=False, arena=True, keep_records=False,
+                                  evaluator=kinds["data/model/" + first[1]], evaluator_p2=kinds["data/model/" + first[2]]))
+    eng.arena(len(rows))
+    games = {int(g["game"]): g for g in eng.games()}
+    names = {1: "player1_wins", 2: "player2_wins", 3: "draw"}
+    for i, (_num, p1, _p2, outcome, move_count) in enumerate(rows):
+        assert names[int(games[i]["outcome"])] == outcome and int(games[i]["move_count"]) == move_count
+        assert int(games[i]["p1_net"]) == (0 if p1 == first[1] else 1)
+    eng.close()
+
+
+def _oracle_games(n_games, budget, terminate_cnt, kind="hash_salted", kind2=None, training=True):
+    out = []
+    for g in range(n_games):
+        gm = O.Game(O.make_cfg(budget=budget, training=training, terminate_cnt=terminate_cnt), kind, kind2, salt=g)
+        gm.play()
+        out.append((gm.records(), gm.outcome, gm.move_count, gm.terminated, gm.total_sims, gm.nn_evals))
+        gm.close()
+    return out
+
+
+@pytest.mark.parametrize("slots,compact", [(24, False), (7, True)])
+def test_concurrent_games_vs_oracle(lib, slots, compact):
+    """many different games in flight (per-game salted stub evaluator), fewer slots than games so
+    that slots are refilled; every record of every game must equal the oracle's bit for bit.
+    The second variant forces the re-root compaction (K5) on every move with a small pool."""
+    n_games, budget, term = 40, 48, 70
+    ref = _oracle_games(n_games, budget, term)
+    eng = lib.Engine(lib.make_cfg(n_slots=slots, budget=budget, training=True, terminate_cnt=term,
+                                  evaluator="hash_salted", compact_always=compact, pool_cap=8192 if compact else 0))
+    st = eng.selfplay(n_games)
+    recs, games = _engine_records(lib, eng)
+    assert len(games) == n_games
+    total_sims = 0
+    for g in range(n_games):
+        rr, outcome, move_count, terminated, sims, evals = ref[g]
+        assert int(games[g]["outcome"]) == outcome and int(games[g]["move_count"]) == move_count
+        assert bool(games[g]["terminated"]) == terminated and int(games[g]["reroot_misses"]) == 0
+        assert int(games[g]["sims"]) == sims and int(games[g]["nn_evals"]) == evals
+        assert len(recs[g]) == len(rr)
+        for a, b in zip(recs[g], rr):
+            assert _same_record(a, b)
+        total_sims += sims
+    assert st["sims"] == total_sims and st["games_finished"] == n_games
+    if compact:
+        assert st["compactions"] > 0
+    eng.close()
+
+
+def test_long_game_draw_rule_vs_oracle(lib):
+    """no ply cap: games run into the 80-ply draw window / long endgames (arena semantics)."""
+    ref = _oracle_games(6, 24, 0, training=False)
+    eng = lib.Engine(lib.make_cfg(n_slots=6, budget=24, training=False, terminate_cnt=0, evaluator="hash_salted",
+                                  keep_records=True, max_plies=4096))
+    eng.selfplay(6)
+    recs, games = _engine_records(lib, eng)
+    for g in range(6):
+        rr, outcome, move_count, _t, sims, _e = ref[g]
+        assert (int(games[g]["outcome"]), int(games[g]["move_count"]), int(games[g]["sims"])) == (outcome, move_count, sims)
+        assert all(_same_record(a, b) for a, b in zip(recs[g], rr)) and len(recs[g]) == len(rr)
+    eng.close()
+
+
+def test_noise_and_temperature_invariants(lib):
+    """epsilon > 0 / tau > 0 use the engine's own Philox streams (no bit parity with numpy's RNG by
+    design); check the structural invariants of the records instead."""
+    eng = lib.Engine(lib.make_cfg(n_slots=16, budget=40, training=True, terminate_cnt=60, evaluator="hash_salted",
+                                  epsilon=0.25, alpha=1.0, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=7))
+    st = eng.selfplay(32)
+    recs, games = _engine_records(lib, eng)
+    assert st["games_finished"] == 32
+    chosen_not_argmax = 0
+    for g, rr in recs.items():
+        outcome = int(games[g]["outcome"])
+        for r in rr:
+            if r["chosen"] < 0:
+                continue
+            assert sum(r["visits"]) == r["root_n"] - 1          # N(node) = 1 + sum N(children)
+            assert r["chosen"] in r["actions"] and -1.0 <= float(r["q"]) <= 1.0
+            player = r["pos"][3] & 1
+            want = 0 if outcome == 3 else (1 if (outcome == 1) == (player == 0) else -1)
+            assert r["z"] == want
+            if r["visits"][r["actions"].index(r["chosen"])] != max(r["visits"]):
+                chosen_not_argmax += 1
+    assert chosen_not_argmax > 0                                 # temperature sampling happened
+    # same seed -> same games; other seed -> different
+    eng2 = lib.Engine(lib.make_cfg(n_slots=5, budget=40, training=True, terminate_cnt=60, evaluator="hash_salted",
+                                   epsilon=0.25, alpha=1.0, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=7))
+    eng2.selfplay(32)
+    recs2, _ = _engine_records(lib, eng2)
+    assert all(len(recs[g]) == len(recs2[g]) and all(_same_record(a, b) for a, b in zip(recs[g], recs2[g])) for g in recs)
+    eng.close()
+    eng2.close()
+
+
+# ---- K4 -------------------------------------------------------------------------------------
+def test_rollout_properties(lib):
+    pos = _pos_arr(lib, [O.start_position()] * 4096)
+    outcome, plies = lib.rollout(pos, seed=3)
+    assert set(np.unique(outcome)) <= {1, 2, 3} and (plies > 10).all()
+    o2, p2 = lib.rollout(pos, seed=3)
+    assert (o2 == outcome).all() and (p2 == plies).all()
+    ref = [O.random_playout(O.start_position(), 1000 + i) for i in range(600)]
+    ref_plies = np.mean([r[1] for r in ref])
+    assert abs(plies.mean() - ref_plies) < 0.1 * ref_plies      # same rules => same playout-length statistics
+    capped, cp = lib.rollout(pos[:64], seed=3, max_plies=5)
+    assert (cp <= 5).all()
+
+
+# ---- K3 -------------------------------------------------------------------------------------
+def _random_leaves(lib, n, seed):
+    rng = np.random.RandomState(seed)
+    leaves = np.zeros(n, dtype=lib.LEAF_DTYPE)
+    planes = np.zeros((n, 8, 8, 14), dtype=np.float32)
+    i = 0
+    while i < n:
+        pos = O.start_position()
+        for _ply in range(rng.randint(1, 140)):
+            kids, mask, st, p5 = O.movegen(pos)
+            if st != codec.ONGOING:
+                break
+            pos = kids[rng.randint(len(kids))]
+        kids, mask, st, p5 = O.movegen(pos)
+        if rng.rand() < 0.3:
+            p5 = rng.randint(0, 81)
+        leaves[i] = (pos[0], pos[1], pos[2], (pos[3] & 1) | (p5 << 8), mask)
+        planes[i] = codec.nn_input_planes(pos, mask, p5)
+        i += 1
+    return leaves, planes
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_net_forward_vs_torch(lib, impl):
+    from ckb200 import net as N
+    from oracle import net_oracle as NO
+    for seed, jitter in ((0, 0.0), (1, 0.2)):
+        blob = N.random_init_blob(seed, jitter)
+        net = lib.Net(0, impl)
+        net.set_weights(blob)
+        leaves, planes = _random_leaves(lib, 97, seed)
+        pol, val = net.forward(leaves)
+        rp, rv = NO.forward(N.unpack(blob), planes)
+        assert np.abs(pol - rp).max() < NET_TOL and np.abs(val - rv).max() < NET_TOL
+        assert np.abs(pol.sum(1) - 1).max() < 1e-5
+        kp, kv = net.predict(planes)                               # Keras-signature entry point
+        assert kp.tobytes() == pol.tobytes() and kv.reshape(-1).tobytes() == val.tobytes()
+        net.close()
+
+
+def test_selfplay_with_network(lib):
+    """whole path with the real network evaluator: games finish, records are consistent."""
+    from ckb200 import net as N
+    net = lib.Net(0)
+    net.set_weights(N.random_init_blob(0))
+    eng = lib.Engine(lib.make_cfg(n_slots=32, budget=30, training=True, terminate_cnt=40, evaluator="net",
+                                  epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10))
+    eng.set_net(0, net)
+    st = eng.selfplay(32)
+    recs, games = _engine_records(lib, eng)
+    assert st["games_finished"] == 32 and st["nn_evals"] > 0 and st["sims"] >= 32 * 30
+    for g, rr in recs.items():
+        for r in rr:
+            if r["chosen"] >= 0:
+                assert sum(r["visits"]) == r["root_n"] - 1
+    eng.close()
+    net.close()
