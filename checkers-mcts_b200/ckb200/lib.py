@@ -47,7 +47,7 @@ class RunStats(C.Structure):
     _fields_ = [("sims", C.c_uint64), ("nn_evals", C.c_uint64), ("steps", C.c_uint64),
                 ("games_finished", C.c_uint64), ("moves", C.c_uint64), ("nodes_created", C.c_uint64),
                 ("compactions", C.c_uint64), ("gpu_ms", C.c_double), ("eval_ms", C.c_double),
-                ("kernel_launches", C.c_uint64)]
+                ("tower_ms", C.c_double), ("kernel_launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -98,6 +98,7 @@ def _load():
     L.ck_records_count.argtypes = [vp]
     L.ck_records_count.restype = i64
     L.ck_records_fetch.argtypes = [vp, vp, i64]
+    L.ck_records_fetch_new.argtypes = [vp, vp, i64, vp, vp]
     L.ck_engine_set_profile.argtypes = [vp, C.c_int]
     L.ck_tree_set_root.argtypes = [vp, vp, i32]
     L.ck_tree_search.argtypes = [vp, i32]
@@ -284,6 +285,14 @@ class Engine(object):
         if n:
             check(_lib.ck_records_fetch(self._h, _ptr(out), len(out)))
         return out[:n]
+
+    def records_new(self, buf):
+        """records of games finished since the last call, written into ``buf`` (RECORD_DTYPE array);
+        -> (n_records, n_games)"""
+        n = C.c_int64()
+        g = C.c_int64()
+        check(_lib.ck_records_fetch_new(self._h, _ptr(buf), len(buf), C.byref(n), C.byref(g)))
+        return n.value, g.value
 
     # single-search API (slot 0)
     def tree_set_root(self, pos, parent_player=-1):

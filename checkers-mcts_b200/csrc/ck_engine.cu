@@ -327,9 +327,10 @@ __device__ void compact_tree(const WarpCtx &c, int t, int root) {
     if (c.lane == 0) { dpos[0] = spos[root]; dstat[0] = sstat[root]; }
     __syncwarp();
     int count = 1;
-    for (int head = 0; head < count; head += 32) {
+    for (int head = 0; head < count;) {
+        const int end = min(head + 32, count);           // nodes appended below are handled by later rounds
         const int i = head + c.lane;
-        const bool valid = i < count;
+        const bool valid = i < end;
         const uint32_t link = valid ? dstat[i].w : 0u;
         const int nch = link_nchild(link), ofc = (int)(link & kFcMask);
         int incl = nch;
@@ -345,6 +346,7 @@ __device__ void compact_tree(const WarpCtx &c, int t, int root) {
             dstat[i].w = (link & ~kFcMask) | (uint32_t)nfc;
         }
         count += total;
+        head = end;
         __syncwarp();
     }
     __syncwarp();
@@ -689,7 +691,9 @@ struct ck_engine {
     EngineDev dev;           // device pointers + config, passed by value to the kernels
     ck_net *net[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> prof_ev;   // 3 per round in profile mode: before eval, after tower, after eval
+    std::vector<char> fetched;          // per local game: records already handed out by ck_records_fetch_new
     Counters *h_ctr = nullptr;        // pinned
     int64_t n_games = 0;
     size_t rec_cap = 0, res_cap = 0;
@@ -707,8 +711,7 @@ static void engine_free(ck_engine *e) {
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
-    if (e->evp0) cudaEventDestroy(e->evp0);
-    if (e->evp1) cudaEventDestroy(e->evp1);
+    for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -747,7 +750,6 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     if (cfg->keep_records) d.max_rec = (cfg->terminate_cnt > 0 ? cfg->terminate_cnt : d.max_plies) + 1;
     CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK_E(cudaEventCreate(&e->ev0)); CK_E(cudaEventCreate(&e->ev1));
-    CK_E(cudaEventCreate(&e->evp0)); CK_E(cudaEventCreate(&e->evp1));
     const size_t nodes = (size_t)d.n_slots * 3 * d.cap;
     CK_E(cudaMalloc(&d.pos, nodes * sizeof(uint4)));
     CK_E(cudaMalloc(&d.stat, nodes * sizeof(uint4)));
@@ -835,6 +837,7 @@ int ck_engine_begin(ck_engine *e, int64_t n_games) {
     const int stride = d.cfg.game_id_stride ? d.cfg.game_id_stride : 1;
     d.arena_half = (int32_t)((n_games * stride) / 2);
     e->n_games = n_games;
+    e->fetched.assign((size_t)n_games, 0);
     int rc = engine_reset_slots(e, 0);
     if (rc != CK_OK) return rc;
     e->begun = true;
@@ -890,10 +893,13 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
     CK_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), e->stream));
     sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot, d_tot + 1);
     int launches = 0;
-    float eval_ms = 0.f;
+    double eval_ms = 0.0, tower_ms = 0.0;
     CK_CUDA(cudaEventRecord(e->ev0, e->stream));
     int64_t steps = 0;
     const int check = 16;
+    if (e->profile && e->prof_ev.size() < (size_t)3 * check) {
+        while (e->prof_ev.size() < (size_t)3 * check) { cudaEvent_t ev; CK_CUDA(cudaEventCreate(&ev)); e->prof_ev.push_back(ev); }
+    }
     for (;;) {
         const int64_t chunk = n_steps > 0 ? std::min<int64_t>(check, n_steps - steps) : check;
         for (int64_t i = 0; i < chunk; ++i) {
@@ -901,14 +907,12 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
                 CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));
                 tree_step_kernel<<<(d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, e->stream>>>(d);
                 ++launches;
-                CK_CUDA(cudaEventRecord(e->evp0, e->stream));
+                CK_CUDA(cudaEventRecord(e->prof_ev[3 * i], e->stream));
+                if (e->net[0]) e->net[0]->ev_after_tower = e->prof_ev[3 * i + 1];
                 rc = engine_eval(e, &launches);
+                if (e->net[0]) e->net[0]->ev_after_tower = nullptr;
                 if (rc != CK_OK) { cudaFree(d_tot); return rc; }
-                CK_CUDA(cudaEventRecord(e->evp1, e->stream));
-                CK_CUDA(cudaEventSynchronize(e->evp1));
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, e->evp0, e->evp1);
-                eval_ms += ms;
+                CK_CUDA(cudaEventRecord(e->prof_ev[3 * i + 2], e->stream));
             } else {
                 rc = engine_round(e, &launches);
                 if (rc != CK_OK) { cudaFree(d_tot); return rc; }
@@ -917,6 +921,15 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         steps += chunk;
         rc = engine_poll(e);
         if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+        if (e->profile) {
+            for (int64_t i = 0; i < chunk; ++i) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, e->prof_ev[3 * i], e->prof_ev[3 * i + 2]);
+                if (d.cfg.evaluator == CK_EVAL_NET && cudaEventElapsedTime(&b, e->prof_ev[3 * i], e->prof_ev[3 * i + 1]) == cudaSuccess) tower_ms += b;
+                eval_ms += a;
+            }
+            cudaGetLastError();
+        }
         if (n_steps > 0 && steps >= n_steps) break;
         if (n_steps <= 0 && e->h_ctr->active == 0 && e->h_ctr->batch_count[0] == 0 && e->h_ctr->batch_count[1] == 0) break;
         if (n_steps <= 0 && e->h_ctr->games_finished >= (unsigned long long)e->n_games) break;
@@ -940,6 +953,7 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         stats->compactions = now.compactions - before.compactions;
         stats->gpu_ms = ms;
         stats->eval_ms = eval_ms;
+        stats->tower_ms = tower_ms;
         stats->kernel_launches = (uint64_t)launches;
         stats->sims = tot[2] - tot[0]; stats->nn_evals = tot[3] - tot[1];
     }
@@ -1010,6 +1024,29 @@ int ck_records_fetch(ck_engine *e, ck_record *out, int64_t cap) {
         CK_CUDA(cudaMemcpy(out + k, e->dev.rec + gi * e->dev.max_rec, (size_t)r.n_records * sizeof(ck_record), cudaMemcpyDeviceToHost));
         k += r.n_records;
     }
+    return CK_OK;
+}
+
+// records of the games that finished since the previous call (bench e2e / streaming consumers)
+int ck_records_fetch_new(ck_engine *e, ck_record *out, int64_t cap, int64_t *n_out, int64_t *n_games_out) {
+    if (!e || !e->begun || !n_out) return fail(CK_ERR_ARG, "ck_records_fetch_new: bad arguments");
+    DeviceGuard g(e->dev.cfg.device);
+    std::vector<ck_game_result> all((size_t)e->n_games);
+    CK_CUDA(cudaMemcpy(all.data(), e->dev.results, all.size() * sizeof(ck_game_result), cudaMemcpyDeviceToHost));
+    int64_t k = 0, ng = 0;
+    for (size_t gi = 0; gi < all.size(); ++gi) {
+        const ck_game_result &r = all[gi];
+        if (r.game < 0 || r.outcome < 0 || e->fetched[gi]) continue;
+        if (e->dev.cfg.keep_records && out) {
+            if (k + r.n_records > cap) break;
+            CK_CUDA(cudaMemcpy(out + k, e->dev.rec + gi * e->dev.max_rec, (size_t)r.n_records * sizeof(ck_record), cudaMemcpyDeviceToHost));
+            k += r.n_records;
+        }
+        e->fetched[gi] = 1;
+        ++ng;
+    }
+    *n_out = k;
+    if (n_games_out) *n_games_out = ng;
     return CK_OK;
 }
 

@@ -187,7 +187,6 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
     __shared__ __align__(16) float s_flat[512 * kHeadPB];   // [i][p] during the dense, [p][512] for softmax
     __shared__ float s_wp[128 * 8];
     __shared__ float s_v1[kHeadPB][64];
-    __shared__ float s_h[kHeadPB][64];
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     for (int i = tid; i < 128 * 8; i += 256) s_wp[i] = blob[hp.pol1x1_k + i];
     __syncthreads();
@@ -298,7 +297,6 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
             if (lane == 0) value[base + p] = tanhf(t + blob[hp.val_d2_b]);
         }
     }
-    (void)s_h;
 }
 
 // ---- host side -----------------------------------------------------------------------------
@@ -375,6 +373,7 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
         rc = net_tc_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl);
         if (rc != CK_OK) return rc;
     }
+    if (net->ev_after_tower) CK_CUDA(cudaEventRecord(net->ev_after_tower, stream));
     HeadParams hp{L.pol1x1.kernel, L.pol1x1.bias, L.pol_dense_k, L.pol_dense_b, L.val1x1.kernel, L.val1x1.bias,
                   L.val_d1_k, L.val_d1_b, L.val_d2_k, L.val_d2_b};
     heads_kernel<<<(unsigned)((max_n + kHeadPB - 1) / kHeadPB), 256, 0, stream>>>(

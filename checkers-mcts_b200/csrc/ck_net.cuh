@@ -38,6 +38,7 @@ struct ck_net {
     ck_leaf *d_leaves = nullptr;     // staging for host entry points
     float *d_policy = nullptr, *d_value = nullptr;
     int64_t io_cap = 0;
+    cudaEvent_t ev_after_tower = nullptr;   // profiling hook: recorded between tower and heads
 };
 
 namespace ck {

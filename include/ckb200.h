@@ -166,7 +166,8 @@ typedef struct {
     uint64_t nodes_created;
     uint64_t compactions;
     double   gpu_ms;          /* CUDA-event time of the call on the engine's stream */
-    double   eval_ms;         /* of which inside the evaluator (net) kernels; 0 if not measured */
+    double   eval_ms;         /* of which inside the evaluator kernels (profile mode; else 0) */
+    double   tower_ms;        /* of which inside the tcgen05 tower kernel (profile mode; else 0) */
     uint64_t kernel_launches;
 } ck_run_stats;
 
@@ -185,6 +186,8 @@ int64_t ck_games_finished(ck_engine *);
 int ck_games_fetch(ck_engine *, ck_game_result *out, int64_t cap);
 int64_t ck_records_count(ck_engine *);
 int ck_records_fetch(ck_engine *, ck_record *out, int64_t cap);
+/* records of the games that finished since the previous call; *n_out records, *n_games_out games */
+int ck_records_fetch_new(ck_engine *, ck_record *out, int64_t cap, int64_t *n_out, int64_t *n_games_out);
 /* time the evaluator separately inside ck_engine_run (adds two events per step) */
 int ck_engine_set_profile(ck_engine *, int on);
 
