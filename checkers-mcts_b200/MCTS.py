@@ -1,0 +1,256 @@
+"""Drop-in for the reference's ``MCTS`` / ``MCTS_Node`` (reference MCTS.py:36-430) on top of the
+device engine.  The whole tree lives in GPU memory (structure-of-arrays node pool, libckb200
+``ck_tree_*`` entry points); ``MCTS_Node`` objects are thin views that fetch ``n / w / p`` and
+their children lazily.  Class-level configuration, method names, argument meaning and raised
+errors follow the reference:
+
+    MCTS(GAME_ENV=..., UCT_C=..., CONSTRAINT='rollout', BUDGET=..., MULTIPROC=False, NEURAL_NET=True,
+         VERBOSE=..., TRAINING=..., DIRICHLET_ALPHA=..., DIRICHLET_EPSILON=..., TEMPERATURE_TAU=...,
+         TEMPERATURE_DECAY=..., TEMP_DECAY_DELAY=...)
+    root = MCTS_Node(state); MCTS.begin_tree_search(root); best = MCTS.best_child(root)
+    root = MCTS.new_root_node(best)
+
+Differences that are forced by the device design and stated here rather than hidden:
+``game_env.neural_net`` must be a device network (``ckb200.net.KerasLikeNet``) or a stub
+(``ckb200.net.StubNet``) -- an arbitrary host ``predict`` object cannot be called from a CUDA
+kernel and there is no CPU fallback; ``CONSTRAINT='time'`` and the net-less random-rollout mode of
+the reference (``NEURAL_NET=False``, MCTS.py:78-89) are served by ``ckb200.lib.rollout`` (K4), not
+by this class.
+"""
+from datetime import datetime
+
+import numpy as np
+
+from ckb200 import codec
+from ckb200 import lib as _L
+from Checkers import history_counters
+
+
+class MCTS(object):
+    _engine = None
+    _generation = 0          # bumped whenever the device tree is rebuilt from scratch
+    _root_idx = None
+
+    @classmethod
+    def __init__(cls, **kwargs):
+        cls.game_env = kwargs['GAME_ENV']
+        cls.uct_c = kwargs['UCT_C']
+        cls.constraint = kwargs['CONSTRAINT']
+        cls.budget = kwargs['BUDGET']
+        cls.multiproc = kwargs['MULTIPROC']
+        cls.neural_net = kwargs['NEURAL_NET']
+        cls.verbose = kwargs['VERBOSE']
+        cls.training = kwargs['TRAINING']
+        cls.alpha = kwargs['DIRICHLET_ALPHA']
+        cls.epsilon = kwargs['DIRICHLET_EPSILON']
+        cls.tau = kwargs['TEMPERATURE_TAU']
+        cls.tau_decay = kwargs['TEMPERATURE_DECAY']
+        cls.tau_decay_delay = kwargs['TEMP_DECAY_DELAY']
+        cls.seed = kwargs.get('SEED', 1)
+        if cls.constraint != 'rollout':
+            raise ValueError('Invalid MCTS computational constraint!' if cls.constraint != 'time' else
+                             "CONSTRAINT='time' is not supported by the device engine; use 'rollout'")
+        if not cls.neural_net:
+            raise ValueError('NEURAL_NET=False (random rollouts) is served by ckb200.lib.rollout, not by MCTS')
+        cls._close_engine()
+
+    # ---- engine plumbing ---------------------------------------------------------------------
+    @classmethod
+    def _close_engine(cls):
+        if cls._engine is not None:
+            cls._engine.close()
+            cls._engine = None
+
+    @classmethod
+    def _ensure_engine(cls):
+        if cls._engine is not None:
+            return cls._engine
+        net = getattr(cls.game_env, 'neural_net', None)
+        kind = getattr(net, 'ck_evaluator', None)
+        device = getattr(cls.game_env, 'device', 0)
+        if kind is None:
+            raise TypeError('game_env.neural_net must be a ckb200 device network (ckb200.net.KerasLikeNet) or a '
+                            'ckb200.net.StubNet; the search runs on the GPU and cannot call a host predict()')
+        cfg = _L.make_cfg(n_slots=1, budget=cls.budget, device=device, uct_c=cls.uct_c, training=cls.training,
+                          alpha=cls.alpha, epsilon=cls.epsilon, tau=cls.tau, tau_decay=cls.tau_decay,
+                          tau_decay_delay=cls.tau_decay_delay, evaluator=kind, keep_records=False, seed=cls.seed)
+        cls._engine = _L.Engine(cfg)
+        if kind == "net":
+            cls._engine.set_net(0, net.net)
+        cls._net_in_engine = net
+        return cls._engine
+
+    # ---- reference API -----------------------------------------------------------------------
+    @classmethod
+    def get_legal_next_states(cls, history):
+        return cls.game_env.get_legal_next_states(history)
+
+    @classmethod
+    def determine_outcome(cls, node):
+        return cls.game_env.determine_outcome(node.history)
+
+    @classmethod
+    def current_player(cls, state):
+        return cls.game_env.current_player(state)
+
+    @classmethod
+    def begin_tree_search(cls, root_node):
+        """BUDGET new simulations from ``root_node`` on top of any inherited statistics
+        (MCTS.py:210-224)."""
+        start = datetime.now()
+        if getattr(cls, '_net_in_engine', None) is not getattr(cls.game_env, 'neural_net', None):
+            cls._close_engine()                      # the caller swapped game_env.neural_net (tournaments do)
+        eng = cls._ensure_engine()
+        if root_node._generation != cls._generation or root_node._idx is None:
+            # a node that is not part of the device tree: start a fresh tree at its state
+            rev, ply = history_counters(root_node.history)
+            pos = codec.encode_state(root_node.state, rev, ply)
+            hist = cls.game_env.history
+            parent_player = int(hist[-2][4, 0, 0]) if len(hist) >= 2 else -1    # MCTS.py:167-173
+            eng.tree_set_root(pos, parent_player)
+            cls._generation += 1
+            root_node._generation, root_node._idx = cls._generation, 0           # a fresh root is node 0
+        elif root_node._idx != cls._root_idx:
+            eng.tree_reroot(root_node._idx)
+        cls._root_idx = root_node._idx
+        if cls.verbose:
+            print('Starting search!')
+        eng.tree_search(cls.budget)
+        cls.rollout_count = cls.budget
+        root_node._children = None
+        root_node._number_of_visits, root_node._total_reward, _b = eng.tree_root()
+        if cls.verbose:
+            print('Stopped  search after {} rollouts and {} duration!'.format(
+                cls.rollout_count, str(datetime.now() - start)[2:-4]))
+
+    @classmethod
+    def best_child(cls, node, criterion='robust'):
+        """most visited child, or a sample ~ n^(1/tau) while training with tau > 0 (MCTS.py:226-248)"""
+        if cls.neural_net:
+            criterion = 'robust'
+        if criterion != 'robust':
+            raise ValueError('Invalid winner selection criterion!')
+        children = node.children
+        visits = [child.n for child in children]
+        if not cls.training or cls.tau <= 0:
+            return children[int(np.argmax(visits))]
+        expon = [float(n) ** (1 / cls.tau) for n in visits]
+        total = np.sum(expon)
+        probs = [n / total for n in expon]
+        if cls.game_env.move_count > cls.tau_decay_delay:
+            cls.tau -= cls.tau_decay
+            if np.isclose(cls.tau, 0):
+                cls.tau = 0
+        return children[int(np.random.choice(len(children), p=probs))]
+
+    @classmethod
+    def new_root_node(cls, old_root):
+        """walk from the previously chosen node through the states played since (multi-hop aware)
+        to the node of the current game state (MCTS.py:250-295)"""
+        hist = cls.game_env.history
+        new_state = cls.game_env.state
+        counter, state_idx = 1, -3
+        while len(hist) + state_idx >= 0 and \
+                cls.game_env.current_player(hist[-2]) == cls.game_env.current_player(hist[state_idx]):
+            counter += 1
+            state_idx -= 1
+        new_root = old_root
+        for idx in range(-counter, 0, 1):
+            for child in new_root.children:
+                if (child.state[:5] == hist[idx][:5]).all():
+                    new_root = child
+                    break
+        if (new_root.state[:5] == new_state[:5]).all():
+            new_root.parent = None
+            return new_root
+        raise ValueError('All child nodes should be visited!  Consider '
+                         'increasing number of rollouts or comment out this'
+                         'error.')
+
+    @classmethod
+    def print_tree(cls, root_node, max_tree_depth=10):
+        root_depth = root_node.depth
+
+        def walk(node):
+            w = node.w
+            w_str = str(round(float(w), 1) if float(w) % 1 else int(w))
+            print('\t' * (node.depth - root_depth) + '|- ({}/{}) ({:.1f}%)'.format(w_str, node.n, node.pwin))
+            if node.depth - root_depth < max_tree_depth:
+                for child in reversed(node.children):
+                    walk(child)
+        walk(root_node)
+
+
+class MCTS_Node(object):
+    """View of one node of the device tree (API of reference MCTS.py:345-430)."""
+
+    def __init__(self, state, parent=None, initial_state=None):
+        self.state = state
+        self.player = MCTS.current_player(self.state)
+        self.parent = parent
+        if parent:
+            self.history = parent.history.copy()
+            self.history.append(state)
+        else:
+            self.history = [state]
+            if initial_state is not None:
+                self.history.insert(0, initial_state)
+        self.depth = len(self.history)
+        self._children = None
+        self._number_of_visits = 0
+        self._total_reward = 0
+        self._prior_prob = 0
+        self._idx = None                 # node id inside the device tree (-1: its root at creation)
+        self._generation = -1
+        self._status = None
+        self.printed = False
+
+    # -- device-backed fields ------------------------------------------------------------------
+    @property
+    def children(self):
+        if self._children is None:
+            self._children = []
+            if self._idx is not None and self._generation == MCTS._generation and MCTS._engine is not None:
+                for c in MCTS._engine.tree_children(self._idx):
+                    node = MCTS_Node.__new__(MCTS_Node)
+                    node.state = codec.decode_state(c["pos"])
+                    node.player = MCTS.current_player(node.state)
+                    node.parent = self
+                    node.history = self.history + [node.state]
+                    node.depth = self.depth + 1
+                    node._children = None
+                    node._number_of_visits, node._total_reward, node._prior_prob = c["n"], c["w"], c["p"]
+                    node._idx, node._generation, node._status = c["idx"], self._generation, c["terminal"]
+                    node.printed = False
+                    self._children.append(node)
+        return self._children
+
+    @property
+    def terminal(self):
+        if self._status is None:
+            self._status = 0 if MCTS.get_legal_next_states(self.history) else 1
+        return self._status != 0
+
+    @property
+    def unvisited_child_states(self):
+        return [] if (self.children or self.terminal) else MCTS.get_legal_next_states(self.history)
+
+    @property
+    def w(self):
+        return self._total_reward
+
+    @property
+    def n(self):
+        return self._number_of_visits
+
+    @property
+    def q(self):
+        return self.w / self.n if self.n else 0
+
+    @property
+    def p(self):
+        return self._prior_prob
+
+    @property
+    def pwin(self):
+        return np.round((self.q + 1) / 2 * 100, 1)

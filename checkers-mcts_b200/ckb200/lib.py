@@ -104,6 +104,8 @@ def _load():
     L.ck_tree_search.argtypes = [vp, i32]
     L.ck_tree_root.argtypes = [vp, vp, vp, vp]
     L.ck_tree_root_children.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ck_tree_children.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.ck_tree_reroot.argtypes = [vp, i32]
     L.ck_tree_best_child.argtypes = [vp, i32, vp]
     L.ck_tree_advance.argtypes = [vp, i32]
     L.ck_tree_node_count.argtypes = [vp]
@@ -309,16 +311,24 @@ class Engine(object):
         check(_lib.ck_tree_root(self._h, C.byref(n), C.byref(w), C.byref(b)))
         return n.value, np.float32(w.value), b.value
 
-    def tree_root_children(self):
+    def tree_children(self, node=-1):
+        """children of ``node`` (-1: root) -> list of dicts with idx, pos, n, w, p, terminal (CK_* status)"""
+        idx = np.zeros(MAX_CHILDREN, dtype=np.int32)
         pos = np.zeros(MAX_CHILDREN, dtype=POS_DTYPE)
         n = np.zeros(MAX_CHILDREN, dtype=np.uint32)
         w = np.zeros(MAX_CHILDREN, dtype=np.float32)
         p = np.zeros(MAX_CHILDREN, dtype=np.float32)
         st = np.zeros(MAX_CHILDREN, dtype=np.int32)
-        check(_lib.ck_tree_root_children(self._h, _ptr(pos), _ptr(n), _ptr(w), _ptr(p), _ptr(st)))
-        b = self.tree_root()[2]
-        return [dict(pos=tuple(int(v) for v in pos[i]), n=int(n[i]), w=np.float32(w[i]), p=np.float32(p[i]),
-                     terminal=int(st[i])) for i in range(b)]
+        b = C.c_int32()
+        check(_lib.ck_tree_children(self._h, int(node), _ptr(idx), _ptr(pos), _ptr(n), _ptr(w), _ptr(p), _ptr(st), C.byref(b)))
+        return [dict(idx=int(idx[i]), pos=tuple(int(v) for v in pos[i]), n=int(n[i]), w=np.float32(w[i]),
+                     p=np.float32(p[i]), terminal=int(st[i])) for i in range(b.value)]
+
+    def tree_root_children(self):
+        return self.tree_children(-1)
+
+    def tree_reroot(self, node):
+        check(_lib.ck_tree_reroot(self._h, int(node)))
 
     def tree_best_child(self, move_count=0):
         idx = C.c_int32()

@@ -89,8 +89,20 @@ class TorchWeights(object):
         return net
 
 
+class StubNet(object):
+    """Deterministic stub evaluator that exists on the device (parity tests / demos): ``kind`` in
+    'uniform_zero', 'uniform_material', 'hash', 'hash_salted'."""
+
+    def __init__(self, kind):
+        self.ck_evaluator = kind
+
+    def predict(self, x):
+        raise TypeError("StubNet evaluates on the device only (inside the search kernels)")
+
+
 class KerasLikeNet(object):
     """Object with Keras' ``predict`` signature (Checkers.py:433) backed by libckb200."""
+    ck_evaluator = "net"
 
     def __init__(self, blob, device=0, impl=None):
         from . import lib

@@ -1124,22 +1124,28 @@ int ck_tree_root(ck_engine *e, uint32_t *n, float *w, int32_t *n_children) {
     return CK_OK;
 }
 
-int ck_tree_root_children(ck_engine *e, ck_pos *pos, uint32_t *n, float *w, float *p, int32_t *status) {
-    if (!e) return fail(CK_ERR_ARG, "ck_tree_root_children: null engine");
+// children of `node` (-1: the current root) in node.children order; idx receives their node ids
+int ck_tree_children(ck_engine *e, int32_t node, int32_t *idx, ck_pos *pos, uint32_t *n, float *w, float *p,
+                     int32_t *status, int32_t *count) {
+    if (!e || !count) return fail(CK_ERR_ARG, "ck_tree_children: bad arguments");
     EngineDev &d = e->dev;
     DeviceGuard g(d.cfg.device);
     Slot s;
     int rc = manual_slot(e, &s);
     if (rc != CK_OK) return rc;
     const size_t base = (size_t)s.buf[s.cur] * d.cap;
+    if (node < 0) node = s.root[s.cur];
+    if (node >= s.alloc[s.cur]) return fail(CK_ERR_ARG, "ck_tree_children: node id out of range");
     uint4 st;
-    CK_CUDA(cudaMemcpy(&st, d.stat + base + s.root[s.cur], sizeof(st), cudaMemcpyDeviceToHost));
+    CK_CUDA(cudaMemcpy(&st, d.stat + base + node, sizeof(st), cudaMemcpyDeviceToHost));
     const int b = (int)((st.w >> 22) & 63u), fc = (int)(st.w & kFcMask);
+    *count = b;
     if (b == 0) return CK_OK;
     uint4 cs[CK_MAX_CHILDREN], cp[CK_MAX_CHILDREN];
     CK_CUDA(cudaMemcpy(cs, d.stat + base + fc, b * sizeof(uint4), cudaMemcpyDeviceToHost));
     CK_CUDA(cudaMemcpy(cp, d.pos + base + fc, b * sizeof(uint4), cudaMemcpyDeviceToHost));
     for (int i = 0; i < b; ++i) {
+        if (idx) idx[i] = fc + i;
         if (pos) { pos[i].p1 = cp[i].x; pos[i].p2 = cp[i].y; pos[i].k = cp[i].z; pos[i].meta = cp[i].w; }
         if (n) n[i] = cs[i].x;
         if (w) memcpy(w + i, &cs[i].y, 4);
@@ -1149,40 +1155,47 @@ int ck_tree_root_children(ck_engine *e, ck_pos *pos, uint32_t *n, float *w, floa
     return CK_OK;
 }
 
+int ck_tree_root_children(ck_engine *e, ck_pos *pos, uint32_t *n, float *w, float *p, int32_t *status) {
+    int32_t count = 0;
+    return ck_tree_children(e, -1, nullptr, pos, n, w, p, status, &count);
+}
+
 int ck_tree_best_child(ck_engine *e, int32_t move_count, int32_t *index) {
     if (!e || !index) return fail(CK_ERR_ARG, "ck_tree_best_child: bad arguments");
     (void)move_count;                      // temperature sampling is the engine's business; the shim asks for the robust child
     uint32_t n[CK_MAX_CHILDREN];
     int32_t b = 0;
-    int rc = ck_tree_root(e, nullptr, nullptr, &b);
+    int rc = ck_tree_children(e, -1, nullptr, nullptr, n, nullptr, nullptr, nullptr, &b);
     if (rc != CK_OK) return rc;
     if (b == 0) return fail(CK_ERR_STATE, "ck_tree_best_child: root has no children");
-    rc = ck_tree_root_children(e, nullptr, n, nullptr, nullptr, nullptr);
-    if (rc != CK_OK) return rc;
     int best = 0;
     for (int i = 1; i < b; ++i) if (n[i] > n[best]) best = i;     // np.argmax: first maximum (MCTS.py:236-238)
     *index = best;
     return CK_OK;
 }
 
-int ck_tree_advance(ck_engine *e, int32_t child_index) {
-    if (!e) return fail(CK_ERR_ARG, "ck_tree_advance: null engine");
+// MCTS.new_root_node (MCTS.py:281-288): `node` (a node id from ck_tree_children) becomes the root
+// of the same tree and keeps its statistics; its link already names its parent's player.
+int ck_tree_reroot(ck_engine *e, int32_t node) {
+    if (!e) return fail(CK_ERR_ARG, "ck_tree_reroot: null engine");
     EngineDev &d = e->dev;
     DeviceGuard g(d.cfg.device);
     Slot s;
     int rc = manual_slot(e, &s);
     if (rc != CK_OK) return rc;
-    const size_t base = (size_t)s.buf[s.cur] * d.cap;
-    uint4 st;
-    CK_CUDA(cudaMemcpy(&st, d.stat + base + s.root[s.cur], sizeof(st), cudaMemcpyDeviceToHost));
-    const int b = (int)((st.w >> 22) & 63u), fc = (int)(st.w & kFcMask);
-    if (child_index < 0 || child_index >= b) return fail(CK_ERR_ARG, "ck_tree_advance: child index out of range");
-    // MCTS.new_root_node for a one-ply advance (MCTS.py:281-288): the chosen child becomes the
-    // root of the same tree and keeps its statistics; its link already names its parent's player.
-    s.root[s.cur] = fc + child_index;
+    if (node < 0 || node >= s.alloc[s.cur]) return fail(CK_ERR_ARG, "ck_tree_reroot: node id out of range");
+    s.root[s.cur] = node;
     s.phase = PH_HALT; s.sims_done = 0;
     CK_CUDA(cudaMemcpy(d.slots, &s, sizeof(Slot), cudaMemcpyHostToDevice));
     return CK_OK;
+}
+
+int ck_tree_advance(ck_engine *e, int32_t child_index) {
+    int32_t idx[CK_MAX_CHILDREN], b = 0;
+    int rc = ck_tree_children(e, -1, idx, nullptr, nullptr, nullptr, nullptr, nullptr, &b);
+    if (rc != CK_OK) return rc;
+    if (child_index < 0 || child_index >= b) return fail(CK_ERR_ARG, "ck_tree_advance: child index out of range");
+    return ck_tree_reroot(e, idx[child_index]);
 }
 
 int64_t ck_tree_node_count(ck_engine *e) {

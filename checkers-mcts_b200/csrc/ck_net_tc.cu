@@ -8,11 +8,15 @@
 //   * Orientation: D[co][square] = sum_k W[co][k] * act[k][square] -- the weights are the
 //     M = 128 operand (A), one position's 64 squares are the N = 64 operand (B).
 //   * Activations live in shared memory as split fp16 (hi + lo, 2 x 11 significand bits) in
-//     the UMMA K-major no-swizzle core-matrix layout over a ZERO-PADDED 10 x 10 board:
-//     byte offset = chunk(ci/8) * 1616 + (row*10 + col) * 16 + (ci%8)*2.  A 3x3 tap is then
-//     just a different descriptor start address ((kh*10 + kw) * 16 bytes): eight board
-//     columns are the eight 16-byte rows of a core matrix, the next board row is SBO = 160 B
-//     away, the next 8-channel chunk LBO = 1616 B away.  No im2col, no halo logic.
+//     the UMMA K-major no-swizzle core-matrix layout over ZERO-PADDED 10 x 10 boards whose
+//     rows are INTERLEAVED across the P positions of the tile:
+//     byte offset = chunk(ci/8) * LBO + ((P*row + p)*10 + col) * 16 + (ci%8)*2.
+//     Eight board columns are the eight 16-byte rows of a core matrix; the next 8-row group
+//     (SBO = 160 B) is the same board row of the next position, so ONE MMA covers all P
+//     positions (N = 64*P) and a 3x3 tap is just a different descriptor start address
+//     ((P*kh*10 + kw) * 16 bytes).  No im2col, no halo logic, and the weight operand is read
+//     from shared memory once per P positions (at N = 64 the SS-mode MMA was shared-memory
+//     bound: profiles/r1a_*).
 //   * Weights stream from L2 through a ring of 32 KB stages with 1-D bulk async copies
 //     (cp.async.bulk + mbarrier complete_tx); they are pre-packed on the device, once per
 //     ck_net_set_weights, as split fp16 core matrices in exactly the stage order.
@@ -28,16 +32,13 @@
 //     warps 2-5 epilogue.  mbarriers: full/empty per weight stage, acc_full (MMA->epilogue),
 //     act_ready (epilogue->MMA).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "ck_net.cuh"
 
 namespace ck {
 namespace tc {
 
-constexpr int kStages = 3;
 constexpr int kStageBytes = 32768;                 // 128 co x 64 ci x (hi + lo) fp16
-constexpr int kChunkStride = 1616;                 // 100 padded squares x 16 B + 16 B pad (bank spread)
-constexpr int kSplitBytes = 16 * kChunkStride;     // one position, hi or lo
-constexpr int kPosBytes = 2 * kSplitBytes;
 constexpr int kThreads = 192;
 constexpr float kActScale = 16.0f;                 // activations are stored as a * 2^4
 constexpr int kLayer0Stages = 9, kLayerStages = 18;
@@ -46,8 +47,17 @@ constexpr size_t kLayer0Bytes = (size_t)kLayer0Stages * kLayer0StageBytes;
 constexpr size_t kLayerBytes = (size_t)kLayerStages * kStageBytes;
 constexpr size_t kPackBytes = kLayer0Bytes + 7 * kLayerBytes;
 
-template <int P> struct Cfg {
-    static constexpr int kActBytes = P * kPosBytes;
+template <int P, int S> struct Cfg {
+    static constexpr int kStages = S;                           // weight ring depth
+    static constexpr int kChunkStride = P * 1600 + 16;          // P x 100 padded squares x 16 B + 16 B pad (bank spread)
+    static constexpr int kSplitBytes = 16 * kChunkStride;       // all 128 channels, hi or lo
+    static constexpr int kActBytes = 2 * kSplitBytes;
+    static constexpr int kN = 64 * P;                           // MMA N: all positions of the tile
+    // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), A and B
+    // F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((128u >> 4) << 24);
+    // byte offset of (position p, padded row r, padded column c) inside one chunk
+    __host__ __device__ static constexpr int sq_off(int p, int r, int c) { return ((P * r + p) * 10 + c) * 16; }
     static constexpr int kTmemCols = P * 64 <= 32 ? 32 : P * 64 <= 64 ? 64 : P * 64 <= 128 ? 128 : P * 64 <= 256 ? 256 : 512;
     static constexpr int kBarOff = kActBytes + kStages * kStageBytes;
     static constexpr int kSmem = kBarOff + 256;
@@ -100,9 +110,6 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), A and B
-// F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
     uint32_t r[16];
@@ -138,10 +145,11 @@ __device__ __forceinline__ void stage_info(int layer, int st, size_t &off, uint3
     }
 }
 
-template <int P>
+template <int P, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 tower_tc_kernel(const TowerParams prm) {
-    using C = Cfg<P>;
+    using C = Cfg<P, S>;
+    constexpr int kStages = S;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n = prm.max_n;
@@ -211,20 +219,16 @@ tower_tc_kernel(const TowerParams prm) {
                         stage_info(layer, st, off, bytes, ksteps, tap, chunk0);
                         const uint32_t a_base = smem_u32(s_w + slot * kStageBytes);
                         const uint32_t a_split = bytes >> 1;                       // hi block, then lo block
-                        const uint32_t tap_off = (uint32_t)((tap / 3) * 10 + (tap % 3)) * 16u;
+                        const uint32_t tap_off = (uint32_t)C::sq_off(0, tap / 3, tap % 3);
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t a_hi = make_desc(a_base + ks * 4096, 2048, 128);
                             const uint64_t a_lo = make_desc(a_base + a_split + ks * 4096, 2048, 128);
-#pragma unroll
-                            for (int p = 0; p < P; ++p) {
-                                const uint32_t b_addr = act_base + p * kPosBytes + (chunk0 + 2 * ks) * kChunkStride + tap_off;
-                                const uint64_t b_hi = make_desc(b_addr, kChunkStride, 160);
-                                const uint64_t b_lo = make_desc(b_addr + kSplitBytes, kChunkStride, 160);
-                                const uint32_t d = tmem_base + (uint32_t)(p * 64);
-                                tc_mma(d, a_hi, b_hi, kIdesc, (st | ks) != 0 ? 1u : 0u);
-                                tc_mma(d, a_hi, b_lo, kIdesc, 1u);
-                                tc_mma(d, a_lo, b_hi, kIdesc, 1u);
-                            }
+                            const uint32_t b_addr = act_base + (chunk0 + 2 * ks) * C::kChunkStride + tap_off;
+                            const uint64_t b_hi = make_desc(b_addr, C::kChunkStride, 160);
+                            const uint64_t b_lo = make_desc(b_addr + C::kSplitBytes, C::kChunkStride, 160);
+                            tc_mma(tmem_base, a_hi, b_hi, C::kIdesc, (st | ks) != 0 ? 1u : 0u);
+                            tc_mma(tmem_base, a_hi, b_lo, C::kIdesc, 1u);
+                            tc_mma(tmem_base, a_lo, b_hi, C::kIdesc, 1u);
                         }
                         tc_commit(bar_empty(slot));                                // frees the weight stage when the MMAs retire
                         if (st == ns - 1) tc_commit(bar_acc_full);                 // layer complete -> epilogue
@@ -274,9 +278,9 @@ tower_tc_kernel(const TowerParams prm) {
                         hi[e] = __float2half_rn(a);
                         lo[e] = __float2half_rn(a - __half2float(hi[e]));
                     }
-                    uint8_t *dst = s_act + p * kPosBytes + ch * kChunkStride + ((x + 1) * 10 + (y + 1)) * 16;
+                    uint8_t *dst = s_act + ch * C::kChunkStride + C::sq_off(p, x + 1, y + 1);
                     *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
-                    *reinterpret_cast<uint4 *>(dst + kSplitBytes) = *reinterpret_cast<const uint4 *>(lo);
+                    *reinterpret_cast<uint4 *>(dst + C::kSplitBytes) = *reinterpret_cast<const uint4 *>(lo);
                 }
             }
             fence_proxy_async();
@@ -288,33 +292,33 @@ tower_tc_kernel(const TowerParams prm) {
                 const float inv = prm.inv_scale[layer];
                 mbar_wait(bar_acc_full, af_phase); af_phase ^= 1u;
                 tc_fence_after();
+                // accumulator column j = (P*x + p)*8 + y: 16 columns = two (board row, position) groups
+                uint8_t *abase = s_act + (co >> 3) * C::kChunkStride + (co & 7) * 2;
+                float *gbase = nullptr;
+                if (layer >= 6) gbase = (layer == 6 ? prm.trunk : prm.pconv) + ((int64_t)tile * P * kC + co) * 64;
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const int pos = tile * P + p;
-                    float *gout = nullptr;
-                    if (pos < n && layer >= 6) gout = (layer == 6 ? prm.trunk : prm.pconv) + ((int64_t)pos * kC + co) * 64;
-                    uint8_t *abase = s_act + p * kPosBytes + (co >> 3) * kChunkStride + (co & 7) * 2;
+                for (int q = 0; q < C::kN / 16; ++q) {
+                    float v[16];
+                    tmem_ld16(t_lane + (uint32_t)(q * 16), v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float v[16];
-                        tmem_ld16(t_lane + (uint32_t)(p * 64 + q * 16), v);
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(fmaxf(fmaf(v[i], inv, bias), 0.f), sc, sh);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaf(fmaxf(fmaf(v[i], inv, bias), 0.f), sc, sh);
-                        if (gout != nullptr) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4 *>(gout + q * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int h = 0; h < 2; ++h) {
+                        const int g = 2 * q + h, x = g / P, p = g % P;
+                        if (gbase != nullptr && tile * P + p < n) {
+                            float *gout = gbase + (int64_t)p * kC * 64 + x * 8;
+                            *reinterpret_cast<float4 *>(gout) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+                            *reinterpret_cast<float4 *>(gout + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
                         }
                         if (layer < 7) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int sq = q * 16 + i, x = sq >> 3, y = sq & 7;
-                                const float a = v[i] * kActScale;
-                                const __half h = __float2half_rn(a);
-                                const __half l = __float2half_rn(a - __half2float(h));
-                                uint8_t *dst = abase + ((x + 1) * 10 + (y + 1)) * 16;
-                                *reinterpret_cast<__half *>(dst) = h;
-                                *reinterpret_cast<__half *>(dst + kSplitBytes) = l;
+                            for (int y = 0; y < 8; ++y) {
+                                const float a = v[8 * h + y] * kActScale;
+                                const __half hh = __float2half_rn(a);
+                                const __half ll = __float2half_rn(a - __half2float(hh));
+                                uint8_t *dst = abase + C::sq_off(p, x + 1, y + 1);
+                                *reinterpret_cast<__half *>(dst) = hh;
+                                *reinterpret_cast<__half *>(dst + C::kSplitBytes) = ll;
                             }
                         }
                     }
@@ -419,16 +423,17 @@ int net_tc_prepare(ck_net *net) {
     return CK_OK;
 }
 
-template <int P>
+template <int P, int S>
 static int launch_tower(ck_net *net, const tc::TowerParams &prm, int64_t max_n, cudaStream_t stream) {
     static bool attr_done = false;
+    static_assert(tc::Cfg<P, S>::kSmem <= 232448, "tower tile does not fit in shared memory");
     if (!attr_done) {
-        CK_CUDA(cudaFuncSetAttribute(tc::tower_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<P>::kSmem));
+        CK_CUDA(cudaFuncSetAttribute(tc::tower_tc_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<P, S>::kSmem));
         attr_done = true;
     }
     const int64_t tiles = (max_n + P - 1) / P;
     const int grid = (int)std::min<int64_t>(tiles, num_sms(net->device));
-    tc::tower_tc_kernel<P><<<grid, tc::kThreads, tc::Cfg<P>::kSmem, stream>>>(prm);
+    tc::tower_tc_kernel<P, S><<<grid, tc::kThreads, tc::Cfg<P, S>::kSmem, stream>>>(prm);
     CK_CUDA(cudaGetLastError());
     return CK_OK;
 }
@@ -445,7 +450,8 @@ int net_tc_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     prm.plane5 = (const float *)aux + 16;
     for (int i = 0; i < 8; ++i) prm.bias_off[i] = L.conv[i].bias;
     prm.trunk = d_trunk; prm.pconv = d_pconv;
-    int rc = launch_tower<2>(net, prm, max_n, stream);
+    static const int variant = [] { const char *v = getenv("CK_TC_TILE"); return v ? atoi(v) : 3; }();
+    int rc = variant == 2 ? launch_tower<2, 3>(net, prm, max_n, stream) : launch_tower<3, 2>(net, prm, max_n, stream);
     if (rc != CK_OK) return rc;
     if (launches) *launches += 1;
     return CK_OK;

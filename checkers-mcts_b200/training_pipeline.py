@@ -1,0 +1,204 @@
+"""Drop-in for the self-play / tournament entry points of the reference's ``training_pipeline``
+(reference training_pipeline.py:310-600) on the B200 engine.
+
+``generate_Checkers_data(selfplay_kwargs, mcts_kwargs).generate_data()`` and
+``tournament_Checkers(tourney_kwargs, mcts_kwargs).start_tournament()`` keep the reference's
+constructor arguments, file names and file formats (pickled ``[state, probs, q, z]`` lists,
+``tabulate`` fancy_grid tournament tables), so ``train_Checkers.py`` can call them unchanged.
+What differs is where the work happens: all games of all ``NUM_CPUS`` "workers" run concurrently
+on the GPU (one warp per game, batched network evaluation) instead of one game per process.
+
+Networks: ``NN_FN`` / ``NEW_NN_FN`` / ``OLD_NN_FN`` name a weight blob saved by ``save_blob``
+(``.npy``, 1,321,774 float32 in the layout of include/ckb200.h).  Keras ``.h5`` import is a
+"next" row; asking for one raises with that explanation rather than guessing.
+"""
+import os
+import pickle
+from datetime import datetime
+
+import numpy as np
+from tabulate import tabulate
+
+from ckb200 import lib as _L
+from ckb200 import net as _N
+from ckb200 import records as _R
+
+
+def create_timestamp():
+    return datetime.now(tz=None).strftime("%d-%b-%Y(%H:%M:%S)")
+
+
+def save_blob(blob, filename):
+    np.save(filename, np.asarray(blob, dtype=np.float32))
+    return filename if filename.endswith(".npy") else filename + ".npy"
+
+
+def load_blob(filename):
+    """-> float32 weight blob, or an evaluator name for 'stub:<kind>' (tests / demos)"""
+    if isinstance(filename, str) and filename.startswith("stub:"):
+        return filename[5:]
+    if isinstance(filename, str) and filename.endswith(".h5"):
+        raise NotImplementedError("Keras .h5 import is not implemented yet (SURVEY 8f row 2); "
+                                  "convert the weights to a .npy blob (ckb200.net.layout) first")
+    blob = np.load(filename)
+    if blob.size != _N.NET_PARAM_COUNT:
+        raise ValueError("weight blob %s has %d values, expected %d" % (filename, blob.size, _N.NET_PARAM_COUNT))
+    return blob.astype(np.float32).reshape(-1)
+
+
+def load_training_data(filename):
+    with open(filename, 'rb') as file:
+        return pickle.load(file)
+
+
+def record_params(phase, **kwargs):
+    """Document the parameters used in the training pipeline (reference :225-244)."""
+    folders = {'selfplay': 'data/training_data/Checkers_SelfPlay_Params_', 'training': 'data/model/Checkers_Training_Params_',
+               'evaluation': 'data/tournament_results/Checkers_Evaluation_Params_',
+               'final': 'data/final_eval/Checkers_Final_Evaluation_Params_'}
+    if phase not in folders:
+        raise ValueError('Invalid phase!')
+    filename = folders[phase] + create_timestamp() + '.txt'
+    with open(filename, 'w') as file:
+        for key, val in kwargs.items():
+            file.write('{} = {}\n'.format(key, val))
+    return filename
+
+
+def _engine_cfg(mcts_kwargs, n_slots, terminate_cnt, evaluator, evaluator_p2=None, arena=False, keep_records=True,
+                device=0, seed=None, game_id_base=0, game_id_stride=1):
+    if mcts_kwargs.get('CONSTRAINT', 'rollout') != 'rollout':
+        raise ValueError("the device engine only supports CONSTRAINT='rollout'")
+    if not mcts_kwargs.get('NEURAL_NET', True):
+        raise ValueError("NEURAL_NET=False (random rollouts) is served by ckb200.lib.rollout")
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")          # np.random.seed() from OS entropy (:341)
+    return _L.make_cfg(n_slots=n_slots, budget=mcts_kwargs['BUDGET'], device=device, uct_c=mcts_kwargs['UCT_C'],
+                       training=mcts_kwargs['TRAINING'], alpha=mcts_kwargs['DIRICHLET_ALPHA'],
+                       epsilon=mcts_kwargs['DIRICHLET_EPSILON'], tau=mcts_kwargs['TEMPERATURE_TAU'],
+                       tau_decay=mcts_kwargs['TEMPERATURE_DECAY'], tau_decay_delay=mcts_kwargs['TEMP_DECAY_DELAY'],
+                       terminate_cnt=terminate_cnt, seed=seed, evaluator=evaluator, evaluator_p2=evaluator_p2,
+                       arena=arena, keep_records=keep_records, game_id_base=game_id_base, game_id_stride=game_id_stride)
+
+
+def _attach(engine, which, spec, device):
+    if isinstance(spec, str):
+        return None
+    net = _L.Net(device)
+    net.set_weights(spec)
+    engine.set_net(which, net)
+    return net
+
+
+class generate_Checkers_data(object):
+    """Self-play data generation (reference :310-469)."""
+
+    def __init__(self, selfplay_kwargs, mcts_kwargs):
+        self.NUM_SELFPLAY_GAMES = selfplay_kwargs['NUM_SELFPLAY_GAMES']
+        self.TRAINING_ITERATION = selfplay_kwargs['TRAINING_ITERATION']
+        self.TERMINATE_CNT = selfplay_kwargs['TERMINATE_CNT']
+        self.num_cpus = selfplay_kwargs['NUM_CPUS']       # number of "workers": total games = games x workers
+        self.nn_fn = selfplay_kwargs['NN_FN']
+        self.device = selfplay_kwargs.get('DEVICE', 0)
+        self.max_slots = selfplay_kwargs.get('MAX_CONCURRENT_GAMES', 4096)
+        self.seed = selfplay_kwargs.get('SEED')
+        self.mcts_kwargs = mcts_kwargs
+        self.stats = None
+
+    def generate_data(self):
+        """plays NUM_SELFPLAY_GAMES x NUM_CPUS games on the GPU; returns the list of pickle files,
+        one per worker as in the reference (a single name when NUM_CPUS == 1)"""
+        spec = load_blob(self.nn_fn)
+        total = self.NUM_SELFPLAY_GAMES * self.num_cpus
+        cfg = _engine_cfg(self.mcts_kwargs, min(total, self.max_slots), self.TERMINATE_CNT,
+                          spec if isinstance(spec, str) else "net", device=self.device, seed=self.seed)
+        eng = _L.Engine(cfg)
+        net = _attach(eng, 0, spec, self.device)
+        self.stats = eng.selfplay(total)
+        recs, games = eng.records(), eng.games()
+        eng.close()
+        if net is not None:
+            net.close()
+        names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
+        for g in games:
+            print('{} after {} moves!'.format(names[int(g["outcome"])], int(g["move_count"])))
+        timestamp = create_timestamp()
+        filenames = []
+        for proc in range(self.num_cpus):                 # worker p played games [p*N, (p+1)*N)
+            lo, hi = proc * self.NUM_SELFPLAY_GAMES, (proc + 1) * self.NUM_SELFPLAY_GAMES
+            memory = _R.to_reference_list(recs[(recs["game"] >= lo) & (recs["game"] < hi)])
+            filenames.append(self._save_memory(memory, self.TRAINING_ITERATION, timestamp, proc))
+        return filenames if self.num_cpus > 1 else filenames[0]
+
+    def _save_memory(self, memory, iteration, timestamp, process_num):
+        filename = 'data/training_data/Checkers_Data' + str(iteration) + '_' + timestamp + '_P' + str(process_num) + '.pkl'
+        with open(filename, 'wb') as file:
+            pickle.dump(memory, file)
+        return filename
+
+
+class tournament_Checkers(object):
+    """New-net versus old-net arena (reference :472-600)."""
+
+    def __init__(self, tourney_kwargs, mcts_kwargs):
+        self.nn1_fn = tourney_kwargs['NEW_NN_FN']
+        self.nn2_fn = tourney_kwargs['OLD_NN_FN']
+        self.NUM_GAMES = tourney_kwargs['TOURNEY_GAMES']
+        self.num_cpus = tourney_kwargs['NUM_CPUS']
+        self.device = tourney_kwargs.get('DEVICE', 0)
+        self.seed = tourney_kwargs.get('SEED')
+        self.mcts_kwargs = mcts_kwargs
+        self.stats = None
+
+    def _start_tournament(self, process_num=0):
+        """TOURNEY_GAMES games, the new net is player 1 in the first half (:523-528); rows
+        [game#, p1_file, p2_file, outcome, move_count] (:552-553)"""
+        s1, s2 = load_blob(self.nn1_fn), load_blob(self.nn2_fn)
+        ev1 = s1 if isinstance(s1, str) else "net"
+        ev2 = s2 if isinstance(s2, str) else "net"
+        seed = None if self.seed is None else self.seed + process_num
+        cfg = _engine_cfg(self.mcts_kwargs, min(self.NUM_GAMES, 4096), 0, ev1, ev2, arena=True, keep_records=False,
+                          device=self.device, seed=seed)
+        eng = _L.Engine(cfg)
+        nets = [_attach(eng, 0, s1, self.device), _attach(eng, 1, s2, self.device)]
+        self.stats = eng.arena(self.NUM_GAMES)
+        games = eng.games()
+        eng.close()
+        for n in nets:
+            if n is not None:
+                n.close()
+        names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
+        rows = []
+        for g in games:
+            p1, p2 = (self.nn1_fn, self.nn2_fn) if int(g["p1_net"]) == 0 else (self.nn2_fn, self.nn1_fn)
+            rows.append([int(g["game"]) + 1, p1, p2, names[int(g["outcome"])], int(g["move_count"])])
+        return rows
+
+    def start_tournament(self):
+        game_outcomes = []
+        for proc in range(self.num_cpus):                 # each worker plays its own TOURNEY_GAMES (:491-494)
+            game_outcomes.extend(self._start_tournament(proc))
+        filename = self._save_tourney_results(game_outcomes)
+        print('Tournament over!  View results in tournament folder!')
+        return filename
+
+    def _save_tourney_results(self, game_outcomes):
+        fn1, fn2 = game_outcomes[0][1], game_outcomes[0][2]
+        wins = {fn1: 0, fn2: 0}
+        draws = 0
+        for idx, row in enumerate(game_outcomes):
+            row[0] = idx + 1
+            if row[3] == 'player1_wins':
+                wins[row[1]] += 1
+            elif row[3] == 'player2_wins':
+                wins[row[2]] += 1
+            else:
+                draws += 1
+        summary = [[fn1, '{}/{}/{}'.format(wins[fn1], wins[fn2], draws)], [fn2, '{}/{}/{}'.format(wins[fn2], wins[fn1], draws)]]
+        filename = 'data/tournament_results/Tournament_' + create_timestamp() + '.txt'
+        with open(filename, 'w') as file:
+            file.write(tabulate(summary, tablefmt='fancy_grid', headers=['Neural Network', 'Wins/Losses/Draws']))
+            file.write('\n\n')
+            file.write(tabulate(game_outcomes, tablefmt='fancy_grid',
+                                headers=['Game Number', 'Player 1', 'Player 2', 'Outcome', 'Turn Count']))
+        return filename

@@ -1,0 +1,147 @@
+"""GPU tests of the reference-facing Python surface (Checkers / MCTS / training_pipeline drop-ins):
+same names, arguments, file formats and errors as the reference, results identical to the golden
+vectors generated from the unmodified reference."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, codec
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from ckb200 import lib as L
+    L.require_device()
+    import Checkers as C
+    import MCTS as M
+    import training_pipeline as T
+    assert os.path.dirname(C.__file__).endswith("checkers-mcts_b200")
+    return C, M, T
+
+
+MCTS_KW = dict(UCT_C=4, CONSTRAINT='rollout', MULTIPROC=False, NEURAL_NET=True, VERBOSE=False, TRAINING=False,
+               DIRICHLET_ALPHA=1.0, DIRICHLET_EPSILON=0.0, TEMPERATURE_TAU=0, TEMPERATURE_DECAY=0, TEMP_DECAY_DELAY=0)
+
+
+def test_checkers_env_matches_oracle(mods):
+    C, _, _ = mods
+    env = C.Checkers()
+    assert env.state.shape == (15, 8, 8) and env.state.dtype == np.float64
+    assert len(env.legal_next_states) == 7 and env.current_player(env.state) == 'player1'
+    rng = np.random.RandomState(3)
+    for _game in range(3):
+        env.reset()
+        pos = O.start_position()
+        while not env.done:
+            kids, mask, status, p5 = O.movegen(pos)
+            assert len(env.legal_next_states) == len(kids)
+            for st, k in zip(env.legal_next_states, kids):
+                assert (st == codec.decode_state(k)).all()
+            assert [codec.plane_to_bits(env.state[6 + i]) for i in range(8)] == mask
+            assert env.state[5, 0, 0] == p5 / 80
+            i = rng.randint(len(kids))
+            state, outcome, done = env.step(env.legal_next_states[i])
+            pos = kids[i]
+            assert state is env.state and env.history[-1] is state
+        assert env.outcome in ('player1_wins', 'player2_wins', 'draw')
+        assert env.get_legal_next_states(env.history) == []
+    env.reset()
+    with pytest.raises(ValueError, match='Illegal next state'):
+        env.step(np.zeros((15, 8, 8)))
+
+
+def test_mcts_shim_first_search_and_reroot(mods):
+    C, M, _ = mods
+    from ckb200.net import StubNet
+    kat = json.load(open(os.path.join(GOLDEN, "mcts_kat.json")))["hash_first_search"]
+    env = C.Checkers(StubNet("hash"))
+    M.MCTS(GAME_ENV=env, BUDGET=kat["budget"], **MCTS_KW)
+    root = M.MCTS_Node(env.state)
+    assert root.player == 'player1' and not root.terminal and root.depth == 1
+    M.MCTS.begin_tree_search(root)
+    assert root.n == kat["root_n"] and float(root.w) == kat["root_w"]
+    for c, r in zip(root.children, kat["children"]):
+        assert (int(c.state[14, 0, 0]) - 6) * 64 + int(c.state[14, 0, 1]) * 8 + int(c.state[14, 0, 2]) == r["action"]
+        assert c.n == r["n"] and float(c.w) == r["w"] and float(c.p) == r["p"] and c.parent is root
+    best = M.MCTS.best_child(root)
+    assert best.n == max(c.n for c in root.children)
+    env.step(best.state)
+    reply = M.MCTS.best_child(best) if best.children else None
+    assert reply is not None
+    env.step(env.legal_next_states[[i for i, s in enumerate(env.legal_next_states)
+                                    if (s[:5] == reply.state[:5]).all()][0]])
+    new_root = M.MCTS.new_root_node(best)
+    assert (new_root.state[:5] == env.state[:5]).all() and new_root.parent is None
+    inherited = new_root.n
+    M.MCTS.begin_tree_search(new_root)
+    assert new_root.n == inherited + kat["budget"]            # BUDGET new sims on top of inherited statistics
+    assert sum(c.n for c in new_root.children) == new_root.n - 1
+    # a move that is not in the tree raises like the reference
+    env2 = C.Checkers(StubNet("hash"))
+    M.MCTS(GAME_ENV=env2, BUDGET=8, **MCTS_KW)
+    r2 = M.MCTS_Node(env2.state)
+    M.MCTS.begin_tree_search(r2)
+    b2 = M.MCTS.best_child(r2)
+    env2.step(b2.state)
+    env2.step(env2.legal_next_states[-1])
+    env2.step(env2.legal_next_states[-1])
+    with pytest.raises(ValueError, match='All child nodes should be visited'):
+        M.MCTS.new_root_node(b2)
+    with pytest.raises(TypeError):
+        env3 = C.Checkers(object())
+        M.MCTS(GAME_ENV=env3, BUDGET=8, **MCTS_KW)
+        M.MCTS.begin_tree_search(M.MCTS_Node(env3.state))
+
+
+def test_generate_data_pickle_matches_reference_golden(mods, tmp_path, monkeypatch):
+    _, _, T = mods
+    f = np.load(os.path.join(GOLDEN, "selfplay_hash.npz"))
+    meta = json.loads(str(f["meta"]))
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/training_data")
+    kw = dict(MCTS_KW, BUDGET=meta["budget"], TRAINING=True)
+    gen = T.generate_Checkers_data(dict(NUM_SELFPLAY_GAMES=1, TRAINING_ITERATION=3, TERMINATE_CNT=meta["terminate_cnt"],
+                                        NUM_CPUS=1, NN_FN="stub:hash"), kw)
+    fn = gen.generate_data()
+    assert fn.startswith("data/training_data/Checkers_Data3_") and fn.endswith("_P0.pkl")
+    data = T.load_training_data(fn)
+    assert len(data) == len(f["q"])
+    for i, (state, probs, q, z) in enumerate(data):
+        assert state.shape == (15, 8, 8) and state.dtype == np.float64 and probs.shape == (8, 8, 8)
+        planes = [codec.plane_to_bits(state[j]) for j in (0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13)]
+        assert planes == [int(v) for v in f["planes"][i]]
+        assert int(state[4, 0, 0]) == f["player"][i] and (state[4] == state[4, 0, 0]).all()
+        assert state[5, 0, 0] == f["plane5"][i] / 80
+        assert [int(v) for v in state[14, 0, 0:3]] == [int(v) for v in f["action"][i]]
+        assert probs.reshape(512).tobytes() == f["probs"][i].tobytes()
+        assert float(q) == f["q"][i] and z == f["z"][i]
+    # several workers -> one file per worker, games split as in the reference
+    gen = T.generate_Checkers_data(dict(NUM_SELFPLAY_GAMES=2, TRAINING_ITERATION=0, TERMINATE_CNT=20, NUM_CPUS=3,
+                                        NN_FN="stub:hash_salted"), dict(kw, BUDGET=20))
+    fns = gen.generate_data()
+    assert len(fns) == 3 and all(len(T.load_training_data(x)) == 2 * 20 for x in fns)
+    T.record_params('selfplay', A=1)
+    with pytest.raises(ValueError):
+        T.record_params('nonsense')
+
+
+def test_tournament_matches_reference_golden(mods, tmp_path, monkeypatch):
+    _, _, T = mods
+    t = json.load(open(os.path.join(GOLDEN, "tournament.json")))
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/tournament_results")
+    kinds = {v: k for k, v in {"A": "stub:" + t["nets"]["data/model/A"], "B": "stub:" + t["nets"]["data/model/B"]}.items()}
+    tour = T.tournament_Checkers(dict(NEW_NN_FN="stub:" + t["nets"]["data/model/A"], OLD_NN_FN="stub:" + t["nets"]["data/model/B"],
+                                      TOURNEY_GAMES=len(t["outcomes"]), NUM_CPUS=1), dict(MCTS_KW, BUDGET=t["budget"]))
+    rows = tour._start_tournament()
+    for row, ref in zip(rows, t["outcomes"]):
+        assert [row[0], kinds[row[1]], kinds[row[2]], row[3], row[4]] == ref
+    fn = tour.start_tournament()
+    txt = open(fn, encoding="utf-8").read()
+    assert fn.startswith("data/tournament_results/Tournament_") and "Wins/Losses/Draws" in txt and "Turn Count" in txt
