@@ -215,8 +215,10 @@ def run_ours(args, rank, world, local_rank):
     weights.copy_(pinned)
     net.set_weights_device(weights.data_ptr(), weights.numel())
 
+    from ckb200 import dist as D
+    base, stride, _n = D.shard(args.slots * world, rank, world)          # game g -> rank g mod world
     cfg = L.make_cfg(n_slots=args.slots, budget=BUDGET, device=dev, evaluator="net", keep_records=True,
-                     seed=20261017, game_id_base=rank, game_id_stride=world, **MCTS)
+                     seed=20261017, game_id_base=base, game_id_stride=stride, **MCTS)
     eng = L.Engine(cfg)
     eng.set_net(0, net)
     n_games = args.slots * 8                     # staged games: enough refills for any bench length
@@ -277,19 +279,13 @@ def run_ours(args, rank, world, local_rank):
     sims, evals, games, moves, e2e_sims, launches = w.tolist()
 
     # pool finished records on rank 0 (the iteration-end NCCL gather; outside the timed regions)
-    gather_ms = None
+    gather_ms, pooled = None, None
     if world > 1:
+        from ckb200 import dist as D
         recs = eng.records()
-        payload = torch.from_numpy(recs.view(np.uint8).reshape(-1).copy()).to("cuda:%d" % dev)
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda:%d" % dev) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([payload.numel()], dtype=torch.int64, device="cuda:%d" % dev))
-        mx = int(max(s.item() for s in sizes))
-        padded = torch.zeros(mx, dtype=torch.uint8, device="cuda:%d" % dev)
-        padded[:payload.numel()] = payload
         torch.cuda.synchronize()
         g0 = time.time()
-        out = [torch.empty(mx, dtype=torch.uint8, device="cuda:%d" % dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(padded, out, dst=0)
+        pooled = D.gather_records(recs, rank, world, device="cuda:%d" % dev)
         torch.cuda.synchronize()
         gather_ms = 1000.0 * (time.time() - g0)
 
@@ -312,6 +308,7 @@ def run_ours(args, rank, world, local_rank):
     line["clocks"] = clocks
     if gather_ms is not None:
         line["records_gather_ms"] = gather_ms
+        line["records_pooled"] = int(len(pooled))
 
     # roofline of the dominant kernel (the tcgen05 tower; rank 0's own launches)
     peaks = measured_peaks()

@@ -20,16 +20,7 @@ EVAL_KINDS = {"net": EVAL_NET, "uniform_zero": EVAL_UNIFORM_ZERO, "uniform_mater
               "hash": EVAL_HASH, "hash_salted": EVAL_HASH_SALTED}
 NET_IMPL_TC, NET_IMPL_SIMT = 0, 1
 
-POS_DTYPE = np.dtype([("p1", "<u4"), ("p2", "<u4"), ("k", "<u4"), ("meta", "<u4")])
-LEAF_DTYPE = np.dtype([("p1", "<u4"), ("p2", "<u4"), ("k", "<u4"), ("info", "<u4"), ("mask", "<u4", (8,))])
-RECORD_DTYPE = np.dtype([
-    ("pos", POS_DTYPE), ("mask", "<u4", (8,)), ("plane5", "<i4"), ("n_children", "<i4"),
-    ("action", "<u2", (MAX_CHILDREN,)), ("visits", "<u4", (MAX_CHILDREN,)), ("q", "<f4"), ("z", "<i4"),
-    ("root_n", "<u4"), ("root_w", "<f4"), ("chosen", "<i4"), ("game", "<i4"), ("ply", "<i4")])
-GAME_DTYPE = np.dtype([
-    ("game", "<i4"), ("outcome", "<i4"), ("move_count", "<i4"), ("terminated", "<i4"),
-    ("n_records", "<i4"), ("reroot_misses", "<i4"), ("p1_net", "<i4"), ("reserved", "<i4"),
-    ("sims", "<u8"), ("nn_evals", "<u8")])
+from .lib_types import GAME_DTYPE, LEAF_DTYPE, POS_DTYPE, RECORD_DTYPE  # noqa: E402,F401
 
 
 class EngineCfg(C.Structure):

@@ -24,12 +24,12 @@
 //     Whi*Ahi + Whi*Alo + Wlo*Ahi, accumulated in fp32 in TMEM (the dropped Wlo*Alo term is
 //     2^-22 relative).  Weights are scaled per layer by a power of two into fp16's sweet
 //     spot, activations by 2^4; the epilogue undoes both exactly.
-//   * Epilogue (4 warps, one TMEM lane = one output channel per thread): tcgen05.ld,
+//   * Epilogue (8 warps, one TMEM lane = one output channel per thread): tcgen05.ld,
 //     bias + ReLU + folded BatchNorm, re-split to fp16 hi/lo and written IN PLACE into the
 //     activation buffer (the accumulators in TMEM are the second buffer), fp32 copies of
 //     conv6 / policy-conv outputs go to HBM for the heads kernel.
 //   * Warp roles: warp 0 producer (bulk copies), warp 1 MMA issuer + TMEM allocator,
-//     warps 2-5 epilogue.  mbarriers: full/empty per weight stage, acc_full (MMA->epilogue),
+//     warps 2-9 epilogue (two warps per TMEM lane quadrant).  mbarriers: full/empty per weight stage, acc_full (MMA->epilogue),
 //     act_ready (epilogue->MMA).
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -39,7 +39,8 @@ namespace ck {
 namespace tc {
 
 constexpr int kStageBytes = 32768;                 // 128 co x 64 ci x (hi + lo) fp16
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quadrant, each takes half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr float kActScale = 16.0f;                 // activations are stored as a * 2^4
 constexpr int kLayer0Stages = 9, kLayerStages = 18;
 constexpr int kLayer0StageBytes = 8192;            // one tap: 128 co x 16 ci x (hi + lo)
@@ -170,7 +171,7 @@ tower_tc_kernel(const TowerParams prm) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
             mbar_init(bar_acc_full, 1);
-            mbar_init(bar_act_ready, 128);
+            mbar_init(bar_act_ready, 32 * kEpiWarps);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -239,19 +240,19 @@ tower_tc_kernel(const TowerParams prm) {
         }
     } else {
         // ===== epilogue warps: TMEM lane quadrant = warp % 4, one output channel per thread =====
-        const int et = tid - 64;                   // 0..127
-        const int quad = warp & 3;
+        const int et = tid - 64;                   // 0..255
+        const int quad = warp & 3;                 // TMEM lanes 32*quad .. 32*quad+31 (hardware: warp id % 4)
+        const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp drains
         const int co = quad * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t af_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // layer-0 input: planes 0..13 (+2 zero channels) of P positions, thread = (square, chunk)
             {
-                const int sq = et & 63, ch = et >> 6, x = sq >> 3, y = sq & 7;
+                const int sq = et & 63, ch = (et >> 6) & 1, x = sq >> 3, y = sq & 7;
                 const bool dark = ((x ^ y) & 1) != 0;
                 const uint32_t bit = 1u << (4 * x + (y >> 1));
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
+                for (int p = et >> 7; p < P; p += 2) {
                     const int pos = tile * P + p;
                     float v[8];
 #pragma unroll
@@ -297,7 +298,7 @@ tower_tc_kernel(const TowerParams prm) {
                 float *gbase = nullptr;
                 if (layer >= 6) gbase = (layer == 6 ? prm.trunk : prm.pconv) + ((int64_t)tile * P * kC + co) * 64;
 #pragma unroll
-                for (int q = 0; q < C::kN / 16; ++q) {
+                for (int q = half; q < C::kN / 16; q += 2) {
                     float v[16];
                     tmem_ld16(t_lane + (uint32_t)(q * 16), v);
 #pragma unroll

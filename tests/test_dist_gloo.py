@@ -1,0 +1,65 @@
+"""CPU test of the N > 1 host logic with two gloo processes: game sharding and the iteration-end
+record gather (no GPU, no kernels)."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from helpers import PKG, ROOT
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    from ckb200 import dist as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dt = np.dtype([("game", "<i4"), ("ply", "<i4"), ("q", "<f4"), ("visits", "<u4", (5,))])
+    base, stride, n_local = D.shard(11, rank, world)
+    recs = np.zeros(n_local * 3, dtype=dt)              # three records per local game
+    for i in range(n_local):
+        for k in range(3):
+            recs[i * 3 + k] = (base + i * stride, k, rank + 0.5, [rank, i, k, 7, 9])
+    out = D.gather_records(recs, rank, world)
+    if rank == 0:
+        q.put((n_local, out.tobytes(), out.dtype.descr))
+    else:
+        assert out is None
+        q.put((n_local, None, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_two_ranks():
+    from ckb200 import dist as D
+    # every game has exactly one owner, ids are base + i*stride
+    for world in (1, 2, 4, 8):
+        seen = []
+        for r in range(world):
+            base, stride, n = D.shard(4096 + 3, r, world)
+            ids = [base + i * stride for i in range(n)]
+            assert all(D.owner(g, world) == r for g in ids)
+            seen += ids
+        assert sorted(seen) == list(range(4096 + 3))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_locals = sorted(r[0] for r in res)
+    assert n_locals == [5, 6]
+    blob = [r for r in res if r[1] is not None][0]
+    dt = np.dtype([("game", "<i4"), ("ply", "<i4"), ("q", "<f4"), ("visits", "<u4", (5,))])
+    out = np.frombuffer(blob[1], dtype=dt)
+    assert len(out) == 11 * 3
+    assert sorted(set(out["game"].tolist())) == list(range(11))
+    assert (out["q"][out["game"] % 2 == 1] == 1.5).all() and (out["q"][out["game"] % 2 == 0] == 0.5).all()
+    assert (out["visits"][:, 3] == 7).all()

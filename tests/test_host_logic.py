@@ -1,0 +1,74 @@
+"""CPU tests of the host-side Python that sits above the C ABI: state codec, weight-blob layout,
+record conversion to the reference's pickle format, the torch restatement of the network."""
+import os
+
+import numpy as np
+
+from helpers import GOLDEN, codec
+from ckb200 import net as N
+from ckb200 import records as R
+from oracle import oracle as O
+
+
+def test_net_layout_matches_reference_parameter_count():
+    lay = N.layout()
+    assert sum(int(np.prod(s)) for _o, s in lay.values()) == N.NET_PARAM_COUNT == 1321774
+    offs = [o for o, _s in lay.values()]
+    assert offs == sorted(offs) and offs[0] == 0
+    blob = N.random_init_blob(0)
+    p = N.unpack(blob)
+    assert p["conv0/kernel"].shape == (3, 3, 14, 128) and p["policy_head/kernel"].shape == (512, 512)
+    assert (p["conv3/bn_gamma"] == 1).all() and (p["conv3/bias"] == 0).all() and (p["value_dense1/bn_var"] == 1).all()
+    lim = np.sqrt(6.0 / (9 * 128 + 9 * 128))
+    assert np.abs(p["conv1/kernel"]).max() <= lim and np.abs(p["conv1/kernel"]).max() > 0.9 * lim
+    assert (N.random_init_blob(0) == blob).all() and (N.random_init_blob(1) != blob).any()
+
+
+def test_torch_restatement_shapes_and_normalisation():
+    from oracle import net_oracle as NO
+    blob = N.random_init_blob(2, 0.1)
+    x = np.zeros((3, 8, 8, 14), dtype=np.float32)
+    x[0] = codec.nn_input_planes(O.start_position(), O.movegen(O.start_position())[1], 0)
+    x[1, ..., 4] = 1
+    p, v = NO.forward(N.unpack(blob), x)
+    assert p.shape == (3, 512) and v.shape == (3,) and np.allclose(p.sum(1), 1) and (np.abs(v) < 1).all()
+    m = NO.TorchKerasLike(blob)
+    kp, kv = m.predict(x)
+    assert kp.dtype == np.float32 and kv.shape == (3, 1) and np.abs(kp - p).max() < 1e-5
+
+
+def test_record_conversion_matches_reference_pickle_layout():
+    """oracle self-play records -> [state, probs, q, z] must equal the golden reference stream"""
+    f = np.load(os.path.join(GOLDEN, "selfplay_hash.npz"))
+    import json
+    meta = json.loads(str(f["meta"]))
+    g = O.Game(O.make_cfg(budget=meta["budget"], training=True, terminate_cnt=meta["terminate_cnt"]), "hash")
+    g.play()
+    from ckb200 import lib_types as T
+    recs = T.records_from_dicts(g.records())
+    out = R.to_reference_list(recs)
+    assert len(out) == len(f["q"])
+    for i, (state, probs, q, z) in enumerate(out):
+        assert state.shape == (15, 8, 8) and state.dtype == np.float64
+        assert [codec.plane_to_bits(state[j]) for j in (0, 1, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13)] == [int(v) for v in f["planes"][i]]
+        assert probs.reshape(512).tobytes() == f["probs"][i].tobytes()
+        assert float(q) == f["q"][i] and z == f["z"][i]
+    assert isinstance(out[-1][2], int) and out[-1][2] in (0, -1)          # terminal record carries a Python int
+    x, (p, v) = R.training_batch(recs[:5])
+    assert x.shape == (5, 8, 8, 14) and p.shape == (5, 512) and v.shape == (5,)
+    assert v[0] == (float(recs[0]["q"]) + int(recs[0]["z"])) / 2
+
+
+def test_codec_roundtrip_random_positions():
+    rng = np.random.RandomState(0)
+    pos = O.start_position()
+    for _ in range(200):
+        kids, mask, st, p5 = O.movegen(pos)
+        state = codec.decode_state(pos, mask, p5)
+        back = codec.encode_state(state, codec.meta_rev(pos[3]), codec.meta_ply(pos[3]))
+        assert back[:3] == pos[:3] and codec.meta_player(back[3]) == codec.meta_player(pos[3])
+        assert codec.meta_action(back[3]) == codec.meta_action(pos[3])
+        if st != codec.ONGOING:
+            pos = O.start_position()
+        else:
+            pos = kids[rng.randint(len(kids))]
