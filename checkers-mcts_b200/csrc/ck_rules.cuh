@@ -58,27 +58,31 @@ CK_HD bool inb(int v) { return (unsigned)v < 8u; }
 CK_HD int dir_dx(int d) { return (d & 2) ? 1 : -1; }
 CK_HD int dir_dy(int d) { return (d & 1) ? 1 : -1; }
 
-// Which of the four diagonal steps from s are a legal plain move / a legal single hop,
-// ignoring the piece kind.  `empty_land` is the occupancy complement used for landing
-// squares (callers pass the parent's stale board for continuation tests, Checkers.py:219,272).
-CK_HD void sq_dirs(uint32_t opp, uint32_t empty, uint32_t empty_land, int s, uint32_t &mv, uint32_t &jp) {
-    const int x = sq_x(s), y = sq_y(s);
-    mv = 0; jp = 0;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        const int nx = x + dir_dx(d), ny = y + dir_dy(d);
-        if (!inb(nx) || !inb(ny)) continue;
-        const uint32_t nb = 1u << sq_of(nx, ny);
-        if (empty & nb) { mv |= 1u << d; continue; }
-        if (!(opp & nb)) continue;
-        const int lx = nx + dir_dx(d), ly = ny + dir_dy(d);
-        if (!inb(lx) || !inb(ly)) continue;
-        if (empty_land & (1u << sq_of(lx, ly))) jp |= 1u << d;
+// ---- whole-board direction sets by shifts ---------------------------------------------------
+// Rows with even x hold columns 1,3,5,7, rows with odd x columns 0,2,4,6, so the diagonal
+// neighbours of square s are s-4 / s-3 (even row, up), s-5 / s-4 (odd row, up), s+4 / s+5 (even
+// row, down), s+3 / s+4 (odd row, down); two steps along a diagonal are always s -+ 9 / -+ 7.
+constexpr uint32_t kEvenRows = 0x0F0F0F0Fu, kOddRows = 0xF0F0F0F0u;
+constexpr uint32_t kNotCol0 = ~0x11111111u, kNotCol3 = ~0x88888888u;   // c = s & 3
+
+// squares whose neighbour in direction d belongs to T
+CK_HD uint32_t nb_in(int d, uint32_t T) {
+    switch (d) {
+        case 0: return ((T << 4) & kEvenRows) | ((T << 5) & kOddRows & kNotCol0);
+        case 1: return ((T << 3) & kEvenRows & kNotCol3) | ((T << 4) & kOddRows);
+        case 2: return ((T >> 4) & kEvenRows) | ((T >> 3) & kOddRows & kNotCol0);
+        default: return ((T >> 5) & kEvenRows & kNotCol3) | ((T >> 4) & kOddRows);
     }
 }
-
-// directions a piece may use: men only forward (player1 moves +x, Checkers.py:120,131-132)
-CK_HD uint32_t dir_allow(bool king, int player) { return king ? 0xFu : (player == 0 ? 0xCu : 0x3u); }
+// squares whose landing square two steps away in direction d belongs to T
+CK_HD uint32_t land_in(int d, uint32_t T) {
+    switch (d) {
+        case 0: return (T << 9) & kNotCol0;
+        case 1: return (T << 7) & kNotCol3;
+        case 2: return (T >> 7) & kNotCol0;
+        default: return (T >> 9) & kNotCol3;
+    }
+}
 
 // generation order of the directions inside one piece:
 //   man moves  : y+1 then y-1 (Checkers.py:125,145);  man jumps : ydir=-1 then +1 (:214)
@@ -99,6 +103,28 @@ CK_HD Side side_of(const ck_pos &p) {
     s.kings = p.k;
     s.empty = ~(p.p1 | p.p2);
     return s;
+}
+
+// pieces of `own` that may use direction d: kings any, men only forward (player1 moves +x,
+// Checkers.py:120,131-132)
+CK_HD uint32_t movers(uint32_t own, uint32_t kings, int player, int d) {
+    const bool forward = player == 0 ? (d >= 2) : (d < 2);
+    return forward ? own : (own & kings);
+}
+
+// source squares with a legal plain move (mv) / single hop (jp) per direction.  `empty_land` is
+// the emptiness used for landing squares (the parent's stale board in continuation tests,
+// Checkers.py:219,272).
+struct DirSets { uint32_t mv[4], jp[4]; };
+CK_HD DirSets dir_sets(uint32_t own, uint32_t opp, uint32_t kings, uint32_t empty, uint32_t empty_land, int player) {
+    DirSets D;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const uint32_t who = movers(own, kings, player, d);
+        D.mv[d] = who & nb_in(d, empty);
+        D.jp[d] = who & nb_in(d, opp) & land_in(d, empty_land);
+    }
+    return D;
 }
 
 // successor for moving the piece on s in direction d (jump: a single hop)
@@ -122,9 +148,10 @@ CK_HD ck_pos make_child(const ck_pos &par, const Side &sd, int s, int d, bool ju
         // the hopping piece keeps the move iff it can hop again from its landing square:
         // opponent pieces from the child, landing emptiness from the PARENT's stale board
         // (Checkers.py:225-237, 279-281)
-        uint32_t mv, jp;
-        sq_dirs(opp, ~(own | opp), sd.empty, sq_of(tx, ty), mv, jp);
-        if (jp & dir_allow(king, sd.player)) next_player = sd.player;
+        uint32_t again = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) again |= movers(tb, king ? tb : 0u, sd.player, e) & nb_in(e, opp) & land_in(e, sd.empty);
+        if (again) next_player = sd.player;
     }
     ck_pos c;
     c.p1 = sd.player == 0 ? own : opp;
@@ -136,28 +163,9 @@ CK_HD ck_pos make_child(const ck_pos &par, const Side &sd, int s, int d, bool ju
     return c;
 }
 
-// per-square legal direction sets of the side to move
-CK_HD void piece_dirs(const Side &sd, int s, uint32_t &mv, uint32_t &jp) {
-    sq_dirs(sd.opp, sd.empty, sd.empty, s, mv, jp);
-    const uint32_t allow = dir_allow((sd.kings >> s) & 1u, sd.player);
-    mv &= allow; jp &= allow;
-}
-
-CK_HD bool any_jump(const Side &sd) {
-    for (uint32_t rem = sd.own; rem; rem &= rem - 1) {
-        uint32_t mv, jp;
-        piece_dirs(sd, ffs32(rem), mv, jp);
-        if (jp) return true;
-    }
-    return false;
-}
 CK_HD bool any_legal(const Side &sd) {
-    for (uint32_t rem = sd.own; rem; rem &= rem - 1) {
-        uint32_t mv, jp;
-        piece_dirs(sd, ffs32(rem), mv, jp);
-        if (mv | jp) return true;
-    }
-    return false;
+    const DirSets D = dir_sets(sd.own, sd.opp, sd.kings, sd.empty, sd.empty, sd.player);
+    return (D.mv[0] | D.mv[1] | D.mv[2] | D.mv[3] | D.jp[0] | D.jp[1] | D.jp[2] | D.jp[3]) != 0;
 }
 
 // determine_outcome (Checkers.py:306-364) given whether the side to move has a legal move.
@@ -183,47 +191,57 @@ CK_HD int status_of(const ck_pos &p, int *plane5) { return outcome_of(p, any_leg
 
 // child sinks for gen_moves: where (and whether) successor n is materialised
 struct NullSink {
+    CK_HD bool want_any() const { return false; }
     CK_HD bool want(int) const { return false; }
     CK_HD void put(int, const ck_pos &) const {}
 };
 struct ArraySink {
     ck_pos *dst; int cap;
+    CK_HD bool want_any() const { return true; }
     CK_HD bool want(int n) const { return n < cap; }
     CK_HD void put(int n, const ck_pos &c) const { dst[n] = c; }
 };
 struct PickSink {          // keep only successor `target` (random playouts)
     ck_pos *dst; int target;
+    CK_HD bool want_any() const { return true; }
     CK_HD bool want(int n) const { return n == target; }
     CK_HD void put(int, const ck_pos &c) const { *dst = c; }
 };
 
 // Full generation in the reference's list order.  Returns the raw _check_moves count (also
-// for finished games, as the reference does).
+// for finished games, as the reference does).  The legal-action planes are exactly the
+// per-direction source sets; jumps are mandatory and clear the move planes (:197-199).
 template <typename Sink>
 CK_HD int gen_moves(const ck_pos &p, const Sink &sink, uint32_t mask[8]) {
     const Side sd = side_of(p);
-    const bool jump = any_jump(sd);
+    const DirSets D = dir_sets(sd.own, sd.opp, sd.kings, sd.empty, sd.empty, sd.player);
+    const bool jump = (D.jp[0] | D.jp[1] | D.jp[2] | D.jp[3]) != 0;
+    uint32_t use[4];
+    int total = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mask[i] = 0;
+    for (int d = 0; d < 4; ++d) {
+        use[d] = jump ? D.jp[d] : D.mv[d];
+        mask[d] = jump ? 0u : use[d];
+        mask[4 + d] = jump ? use[d] : 0u;
+        total += popc32(use[d]);
+    }
+    if (!sink.want_any()) return total;
+    const uint32_t any = use[0] | use[1] | use[2] | use[3];
     int n = 0;
-    for (int pass = 0; pass < 2; ++pass) {               // men first, then kings (:111-124,168-196,197-199)
+    for (int pass = 0; pass < 2; ++pass) {               // men first, then kings (:111-124,168-196)
         const bool king = pass == 1;
-        for (uint32_t rem = king ? (sd.own & sd.kings) : (sd.own & ~sd.kings); rem; rem &= rem - 1) {
+        for (uint32_t rem = any & (king ? sd.kings : ~sd.kings); rem; rem &= rem - 1) {
             const int s = ffs32(rem);
-            uint32_t mv, jp;
-            piece_dirs(sd, s, mv, jp);
-            const uint32_t use = jump ? jp : mv;
             const int nd = king ? 4 : 2;
             for (int i = 0; i < nd; ++i) {
                 const int d = order_dir(king, jump, sd.player, i);
-                if (!((use >> d) & 1u)) continue;
-                mask[(jump ? 4 : 0) + d] |= 1u << s;
+                if (!((use[d] >> s) & 1u)) continue;
                 if (sink.want(n)) sink.put(n, make_child(p, sd, s, d, jump));
                 ++n;
             }
         }
     }
-    return n;
+    return total;
 }
 
 CK_HD ck_pos start_position() {
