@@ -333,6 +333,8 @@ static int net_finish_weights(ck_net *net) {
     CK_CUDA(cudaGetLastError());
     int rc = net_tc_prepare(net);
     if (rc != CK_OK) return rc;
+    rc = net_ts_prepare(net);
+    if (rc != CK_OK) return rc;
     CK_CUDA(cudaDeviceSynchronize());
     net->have_weights = true;
     return CK_OK;
@@ -370,7 +372,10 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
         trunk = a; pconv = b;
         CK_CUDA(cudaGetLastError());
     } else {
-        rc = net_tc_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl);
+        // CK_TOWER=ss selects the earlier all-shared-memory tcgen05 kernel (cross-check)
+        static const bool use_ss = [] { const char *v = getenv("CK_TOWER"); return v && v[0] == 's'; }();
+        rc = use_ss ? net_tc_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl)
+                    : net_ts_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl);
         if (rc != CK_OK) return rc;
     }
     if (net->ev_after_tower) CK_CUDA(cudaEventRecord(net->ev_after_tower, stream));
@@ -402,7 +407,7 @@ ck_net *ck_net_create(int device) {
 void ck_net_destroy(ck_net *net) {
     if (!net) return;
     DeviceGuard g(net->device);
-    cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack);
+    cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack); cudaFree(net->d_wts);
     cudaFree(net->d_act0); cudaFree(net->d_act1);
     cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value);
     delete net;

@@ -32,6 +32,7 @@ struct ck_net {
     // tcgen05 tower operands (built by ck_net_tc.cu)
     void *d_wpack = nullptr;         // split-fp16 weights in UMMA core-matrix order
     size_t wpack_bytes = 0;
+    void *d_wts = nullptr;           // split-fp16 weights in k-step order for the weights-in-TMEM tower (ck_net_ts.cu)
     // activation scratch, grown on demand
     int64_t cap = 0;
     float *d_act0 = nullptr, *d_act1 = nullptr;   // [cap][128][64] fp32 (SIMT ping-pong / tower outputs)
@@ -57,5 +58,9 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
 // both fp32 [n][128][64]
 int net_tc_prepare(ck_net *net);
 int net_tc_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
+                 float *d_trunk, float *d_pconv, cudaStream_t stream, int *launches);
+// weights-in-TMEM tower (ck_net_ts.cu), same contract; the default tensor-core path
+int net_ts_prepare(ck_net *net);
+int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
                  float *d_trunk, float *d_pconv, cudaStream_t stream, int *launches);
 }  // namespace ck

@@ -1,0 +1,447 @@
+// ck_net_ts.cu -- K3 tower, weights-in-TMEM variant (tcgen05.mma with the A operand in tensor
+// memory), sm_100a.  The product path of ck_net_forward*/the engine; ck_net_tc.cu keeps the
+// earlier all-shared-memory kernel as a cross-check (CK_TOWER=ss).
+//
+// Same arithmetic contract as ck_net_tc.cu: the eight 3x3 convolutions of create_nn (reference
+// training_pipeline.py:57-88) as D[co][square] = sum_k W[co][k] * act[k][square] with split-fp16
+// operands (Whi*Ahi + Whi*Alo + Wlo*Ahi, fp32 accumulation in TMEM), epilogue = bias + ReLU +
+// folded BatchNorm (conv -> bias -> ReLU -> BN, :60-63).  What changed is where the operands live
+// and how the layer-to-layer dependency is hidden:
+//
+//   * WEIGHTS never touch shared memory.  Four loader warps stream the pre-packed split-fp16
+//     weights from L2 with coalesced 16-byte loads (one output channel = one TMEM lane per
+//     thread) and write them with tcgen05.st into a 16-slot ring of TMEM columns [256,512)
+//     (one slot = one k-step = 16 input channels of one tap: 8 columns hi + 8 columns lo).
+//     The MMAs take A from TMEM, so shared-memory bandwidth is spent on the activation (B) operand
+//     only (64 B/clk instead of > 128 B/clk for an N = 128 tile with both operands in smem).
+//   * TWO position tiles (X, Y; 2 positions = N 128 each, accumulators in TMEM columns [0,128)
+//     and [128,256)) share every weight slot.  Y runs kSkew k-steps behind X, so when X finishes
+//     a layer its epilogue overlaps Y's remaining MMAs and then X's next layer overlaps Y's
+//     epilogue: the tensor pipe does not idle across the layer boundary, which was the 17 % +
+//     exposed epilogue of the single-tile kernel (profiles/r1c_tower_ncu_summary.json).
+//   * Activations: shared memory, split fp16 (hi, lo), zero-padded 10 x 10 boards in the UMMA
+//     K-major no-swizzle core-matrix layout with rows interleaved over the 2 positions of a tile
+//     (byte offset = chunk(ci/8)*kChunkStride + ((2*row + p)*10 + col)*16 + (ci%8)*2), so a 3x3 tap
+//     is a descriptor start offset and one MMA covers the whole tile.  2 tiles x 100.5 KB.
+//   * Warp roles: warps 0-3 weight loaders (TMEM lane quadrant = warp), warps 4..4+E-1 epilogue
+//     (quadrant = warp % 4, E/4 warps share a quadrant's columns), last warp MMA issuer + TMEM
+//     allocator.  mbarriers: full/empty per weight slot, acc_full / act_ready per tile.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include "ck_net.cuh"
+#include "ck_tc_ptx.cuh"
+
+namespace ck {
+namespace ts {
+
+using namespace ck::ptx;
+
+constexpr int kP = 2;                               // positions per tile
+constexpr int kN = 64 * kP;                         // MMA N
+constexpr int kChunkStride = kP * 1600 + 16;        // 8 channels x (kP x 100 padded squares) x 2 B + 16 B bank spread
+constexpr int kSplitBytes = 16 * kChunkStride;      // all 128 channels, hi or lo
+constexpr int kTileBytes = 2 * kSplitBytes;
+constexpr int kKSteps0 = 9, kKStepsL = 72;          // k-steps (16 input channels of one tap) per layer
+constexpr int kG = kKSteps0 + 7 * kKStepsL;         // 513 k-steps = the whole weight stream
+constexpr int kNS = 16;                             // TMEM weight ring slots (16 columns each)
+constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
+constexpr int kLoaderWarps = 8;                     // two sets of four (one warp per TMEM lane quadrant)
+constexpr int kLoadGroup = 4;                       // k-steps a loader warp fetches per batch
+constexpr float kActScale = 16.0f;                  // activations are stored as a * 2^4
+constexpr size_t kWtsBytes = (size_t)kG * 8192;     // [k-step][unit 4][co 128][16 B]
+// Every CTA streams the same 4.2 MB in near lock-step, which concentrates the reads of all 148 SMs on
+// the few L2 slices that hold the current window (profiles/r1e: loaders stalled on the loads while
+// lts throughput sat at 7 %).  The packed weights are therefore replicated; CTA b reads copy b % kCopies.
+constexpr int kCopies = 8;
+constexpr uint32_t kIdesc = make_idesc_f16(128, kN);
+constexpr int kBarOff = 2 * kTileBytes;
+constexpr int kSmem = kBarOff + 512;
+
+__host__ __device__ constexpr int sq_off(int p, int r, int c) { return ((kP * r + p) * 10 + c) * 16; }
+
+struct TowerParams {
+    const ck_leaf *leaves;
+    const int32_t *n_dev;
+    int32_t max_n;
+    const uint4 *wts;            // split-fp16 weights, k-step order
+    const float *blob;           // Keras-ordered fp32 parameters (biases)
+    const float *fold;           // folded BN scale/shift table
+    const float *inv_scale;      // per layer 1 / (weight scale * activation scale)
+    int64_t bias_off[8];
+    float *trunk, *pconv;        // fp32 [n][128][64]
+    const float *plane5;         // 81-entry float32(n/80) table
+};
+
+// position of a tile in the weight stream
+struct Cursor {
+    int layer = 0, k = 0;
+    __device__ __forceinline__ int len() const { return layer == 0 ? kKSteps0 : kKStepsL; }
+    __device__ __forceinline__ bool first() const { return k == 0; }
+    __device__ __forceinline__ bool last() const { return k == len() - 1; }
+    __device__ __forceinline__ int tap() const { return layer == 0 ? k : (k >> 3); }
+    __device__ __forceinline__ int chunk0() const { return layer == 0 ? 0 : ((k & 7) << 1); }
+    __device__ __forceinline__ void advance() {
+        if (++k == len()) { k = 0; layer = layer == kTowerConvs - 1 ? 0 : layer + 1; }
+    }
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int kEpiWarps>
+__global__ void __launch_bounds__((kLoaderWarps + 2 + kEpiWarps) * 32, 1)
+tower_ts_kernel(const TowerParams prm) {
+    static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
+    constexpr int kMmaWarp0 = kLoaderWarps + kEpiWarps;            // warps kMmaWarp0 (tile X) and kMmaWarp0 + 1 (tile Y)
+    constexpr int kRowsPer = 8 / (kEpiWarps / 4);       // board rows (16 accumulator columns each) per epilogue warp
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n = prm.max_n;
+    if (prm.n_dev != nullptr) n = min(n, *prm.n_dev);
+    const int n_pairs = (n + 2 * kP - 1) / (2 * kP);
+    if ((int)blockIdx.x >= n_pairs) return;
+    const uint32_t np = (uint32_t)(n_pairs - 1 - (int)blockIdx.x) / gridDim.x + 1;   // tile pairs of this CTA
+    const uint32_t total = np * (uint32_t)kG;                                        // k-steps this CTA streams
+
+    const uint32_t bar0 = smem_u32(smem + kBarOff);
+    auto bar_full = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](uint32_t s) { return bar0 + 8u * (kNS + s); };
+    auto bar_acc_full = [&](int t) { return bar0 + 8u * (2 * kNS + t); };
+    auto bar_act_ready = [&](int t) { return bar0 + 8u * (2 * kNS + 2 + t); };
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kBarOff + 8 * (2 * kNS + 4));
+
+    for (int i = tid * 16; i < 2 * kTileBytes; i += (int)blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
+    if (warp == kMmaWarp0) {
+        if (lane == 0) {
+            for (int s = 0; s < kNS; ++s) { mbar_init(bar_full(s), 4); mbar_init(bar_empty(s), 2); }
+            for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 32 * kEpiWarps); }
+            mbar_init_fence();
+        }
+        __syncwarp();
+        tmem_alloc<512>(smem_u32(s_tmem));
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // the CTA owns all 512 columns, so the allocation starts at column 0, lane 0; the role code below
+    // uses literal TMEM addresses (keeps the MMA operands provably warp-uniform)
+    if (*s_tmem != 0u) __trap();
+
+    if (warp < kLoaderWarps) {
+        // ===== weight loaders: L2 -> registers -> TMEM ring (lane = output channel).  Two sets of four
+        // warps (one warp per TMEM lane quadrant) alternate groups of kLoadGroup k-steps: a warp has
+        // ONE batch of loads in flight at a time (ptxas puts every LDG of a warp on the same
+        // scoreboard, so deeper per-warp prefetch does not overlap), and the other set's batch covers
+        // its latency. =====
+        const int set = warp >> 2, quad = warp & 3;
+        const uint4 *src = prm.wts + (size_t)(blockIdx.x % kCopies) * (kWtsBytes / 16) + (quad * 32 + lane);
+        const uint32_t t_w = ((uint32_t)(quad * 32) << 16) + kWCol0;
+        uint32_t r[kLoadGroup][16];
+        for (uint32_t base = (uint32_t)(set * kLoadGroup); base < total; base += 2 * kLoadGroup) {
+#pragma unroll
+            for (int j = 0; j < kLoadGroup; ++j) {
+                const uint32_t g = (base + j) % (uint32_t)kG;            // reads past `total` stay inside the stream
+                const uint4 *p = src + (size_t)g * 512;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint4 v = ld_stream(p + u * 128);
+                    r[j][4 * u] = v.x; r[j][4 * u + 1] = v.y; r[j][4 * u + 2] = v.z; r[j][4 * u + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kLoadGroup; ++j) {
+                const uint32_t ss = base + j;
+                if (ss < total) {
+                    const uint32_t slot = ss % kNS;
+                    mbar_wait(bar_empty(slot), ((ss / kNS) & 1u) ^ 1u);
+                    tc_fence_after();
+                    tmem_st16(t_w + slot * 16, r[j]);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < kLoadGroup; ++j)
+                    if (base + j < total) mbar_arrive(bar_full((base + j) % kNS));
+            }
+        }
+    } else if (warp >= kMmaWarp0) {
+        // ===== MMA issuers, one warp per tile.  The whole warp runs the loop converged; elect.sync
+        // inside the wrappers picks the issuing lane.  The two warps are not ordered against each
+        // other: whichever tile is in its epilogue leaves the tensor pipe to the other one, and the
+        // 16-slot weight ring bounds how far they drift apart. =====
+        const int t = warp - kMmaWarp0;
+        // trip count from kernel parameters and special registers only, so that the loop state (k-step
+        // counter, descriptors, TMEM addresses) stays in uniform registers; the device-side batch count
+        // only shortens the loop through the break below
+        const uint32_t npu = (uint32_t)((prm.max_n + 2 * kP - 1) / (2 * kP) - 1 - (int)blockIdx.x) / gridDim.x + 1;
+        const uint32_t tile16 = (smem_u32(smem) + (uint32_t)(t * kTileBytes)) >> 4;      // tile base in 16-byte units
+        constexpr uint32_t kDescLo = (uint32_t)(kChunkStride >> 4) << 16;                   // LBO
+        constexpr uint64_t kDescHi = ((uint64_t)((160u >> 4) | (1u << 14))) << 32;          // SBO, descriptor version
+        const uint32_t d = (uint32_t)(t * kN);
+        uint32_t s = 0, ar_phase = 0;
+        for (uint32_t pair = 0; pair < npu; ++pair) {
+            if (pair >= np) break;
+            for (int layer = 0; layer < kTowerConvs; ++layer) {
+                mbar_wait(bar_act_ready(t), ar_phase); ar_phase ^= 1u;
+                tc_fence_after();
+                const int nk = layer == 0 ? 1 : 8;
+                uint32_t acc = 0u;
+                for (int tr = 0; tr < 3; ++tr) {
+                    for (int tcl = 0; tcl < 3; ++tcl) {
+                        uint32_t b = tile16 + (uint32_t)(kP * tr * 10 + tcl);           // sq_off(0, tr, tcl) / 16
+#pragma unroll 1
+                        for (int kc = 0; kc < nk; ++kc, ++s) {
+                            const uint32_t slot = s & (kNS - 1);
+                            mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                            tc_fence_after();
+                            tc_kstep_ts_elect(d, kWCol0 + slot * 16, kDescHi | (uint64_t)(kDescLo + b), (uint32_t)(kSplitBytes >> 4), kIdesc, acc,
+                                              bar_empty(slot));            // 2 arrivals (X and Y) free the slot
+                            acc = 1u;
+                            b += (uint32_t)(2 * kChunkStride) >> 4;
+                        }
+                    }
+                }
+                tc_commit_elect(bar_acc_full(t));
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4, one output channel per thread.  Every
+        // warp serves both tiles and takes whichever accumulator is complete first. =====
+        const int ew = warp - kLoaderWarps, et = tid - kLoaderWarps * 32;
+        const int quad = warp & 3, sub = ew >> 2;
+        const int co = quad * 32 + lane;
+        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+
+        auto build_input = [&](int t, uint32_t k) {
+            // planes 0..13 (+2 zero channels) of the tile's positions, thread = (square, chunk, position)
+            if (et < 64 * 2 * kP) {
+                const int sq = et & 63, ch = (et >> 6) & 1, p = et >> 7, x = sq >> 3, y = sq & 7;
+                const bool dark = ((x ^ y) & 1) != 0;
+                const uint32_t bit = 1u << (4 * x + (y >> 1));
+                const int64_t pos = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * (2 * kP) + t * kP + p;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                if (pos < n) {
+                    const ck_leaf L = prm.leaves[pos];
+                    if (ch == 0) {
+                        if (dark) {
+                            v[0] = (L.p1 & ~L.k & bit) ? 1.f : 0.f; v[1] = (L.p1 & L.k & bit) ? 1.f : 0.f;
+                            v[2] = (L.p2 & ~L.k & bit) ? 1.f : 0.f; v[3] = (L.p2 & L.k & bit) ? 1.f : 0.f;
+                            v[6] = (L.mask[0] & bit) ? 1.f : 0.f; v[7] = (L.mask[1] & bit) ? 1.f : 0.f;
+                        }
+                        v[4] = (float)(L.info & 1u);
+                        v[5] = prm.plane5[(L.info >> 8) & 0xFFu];
+                    } else if (dark) {
+#pragma unroll
+                        for (int e = 0; e < 6; ++e) v[e] = (L.mask[2 + e] & bit) ? 1.f : 0.f;
+                    }
+                }
+                __half hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float a = v[e] * kActScale;
+                    hi[e] = __float2half_rn(a);
+                    lo[e] = __float2half_rn(a - __half2float(hi[e]));
+                }
+                uint8_t *dst = smem + t * kTileBytes + ch * kChunkStride + sq_off(p, x + 1, y + 1);
+                *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(dst + kSplitBytes) = *reinterpret_cast<const uint4 *>(lo);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_act_ready(t));
+        };
+
+        build_input(0, 0);
+        build_input(1, 0);
+        // per tile: next event = (pair ek, layer el), acc_full phase ph   (scalars: a runtime tile index
+        // into arrays would put them in local memory)
+        uint32_t ek0 = 0u, ek1 = 0u, ph0 = 0u, ph1 = 0u;
+        int el0 = 0, el1 = 0;
+        while (ek0 < np || ek1 < np) {
+            int t = -1;
+            if (ek0 < np && __any_sync(0xFFFFFFFFu, mbar_test(bar_acc_full(0), ph0))) t = 0;
+            else if (ek1 < np && __any_sync(0xFFFFFFFFu, mbar_test(bar_acc_full(1), ph1))) t = 1;
+            if (t < 0) { __nanosleep(32); continue; }
+            const int layer = t ? el1 : el0;
+            const uint32_t k = t ? ek1 : ek0;
+            if (t) ph1 ^= 1u; else ph0 ^= 1u;
+            tc_fence_after();
+            const float bias = prm.blob[prm.bias_off[layer] + co];
+            const float sc = prm.fold[kScaleTower + layer * 2 * kC + co] * kActScale;
+            const float sh = prm.fold[kScaleTower + layer * 2 * kC + kC + co] * kActScale;
+            const float inv = prm.inv_scale[layer];
+            // accumulator column j = (2*x + p)*8 + y: 16 columns = board row x of both positions
+            uint8_t *abase = smem + t * kTileBytes + (co >> 3) * kChunkStride + (co & 7) * 2;
+            const int64_t pos0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * (2 * kP) + t * kP;
+            float *gbase = nullptr;
+            if (layer >= 6) gbase = (layer == 6 ? prm.trunk : prm.pconv) + (pos0 * kC + co) * 64;
+            const uint32_t t_acc = t_lane + (uint32_t)(t * kN);
+            const int x0 = sub * kRowsPer;
+            uint32_t ra[16], rb[16];
+            tmem_ld16_async(t_acc + (uint32_t)(x0 * 16), ra);
+#pragma unroll
+            for (int i = 0; i < kRowsPer; ++i) {
+                uint32_t *cur = (i & 1) ? rb : ra, *nxt = (i & 1) ? ra : rb;
+                tmem_ld_wait16(cur);
+                if (i + 1 < kRowsPer) tmem_ld16_async(t_acc + (uint32_t)((x0 + i + 1) * 16), nxt);
+                const int x = x0 + i;
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    float a[8];
+#pragma unroll
+                    for (int y = 0; y < 8; ++y)
+                        a[y] = fmaf(fmaxf(fmaf(__uint_as_float(cur[8 * p + y]), inv, bias), 0.f), sc, sh);
+                    if (gbase != nullptr && pos0 + p < n) {
+                        float *gout = gbase + (int64_t)p * kC * 64 + x * 8;
+                        constexpr float q = 1.0f / kActScale;
+                        *reinterpret_cast<float4 *>(gout) = make_float4(a[0] * q, a[1] * q, a[2] * q, a[3] * q);
+                        *reinterpret_cast<float4 *>(gout + 4) = make_float4(a[4] * q, a[5] * q, a[6] * q, a[7] * q);
+                    }
+                    if (layer < kTowerConvs - 1) {
+                        uint8_t *dst = abase + sq_off(p, x + 1, 1);
+#pragma unroll
+                        for (int y = 0; y < 8; y += 2) {
+                            const __half2 h = __floats2half2_rn(a[y], a[y + 1]);
+                            const float2 f = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(a[y] - f.x, a[y + 1] - f.y);
+                            *reinterpret_cast<__half *>(dst + y * 16) = __low2half(h);
+                            *reinterpret_cast<__half *>(dst + (y + 1) * 16) = __high2half(h);
+                            *reinterpret_cast<__half *>(dst + kSplitBytes + y * 16) = __low2half(l);
+                            *reinterpret_cast<__half *>(dst + kSplitBytes + (y + 1) * 16) = __high2half(l);
+                        }
+                    }
+                }
+            }
+            if (layer < kTowerConvs - 1) {
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_act_ready(t));
+                if (t) el1 = layer + 1; else el0 = layer + 1;
+            } else {
+                tc_fence_before();
+                if (t) { el1 = 0; ek1 = k + 1; } else { el0 = 0; ek0 = k + 1; }
+                if (k + 1 < np) build_input(t, k + 1);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp0) tmem_dealloc<512>(0u);
+}
+
+// ---- weight packing (once per ck_net_set_weights) ---------------------------------------------
+struct PackAux { int64_t koff[8]; int cin[8]; };
+
+// per layer: power-of-two scale S with max|w| * S in [8192, 16384)
+__global__ void wscale_kernel(const float *__restrict__ blob, PackAux aux, float *__restrict__ wscale, float *__restrict__ inv_scale) {
+    const int layer = blockIdx.x;
+    const int64_t n = (int64_t)9 * aux.cin[layer] * kC;
+    const float *w = blob + aux.koff[layer];
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    __shared__ float s_m[256];
+    s_m[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) { if ((int)threadIdx.x < o) s_m[threadIdx.x] = fmaxf(s_m[threadIdx.x], s_m[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) {
+        m = s_m[0];
+        int e = 0;
+        if (m > 0.f && isfinite(m)) { int ex; frexpf(m, &ex); e = 14 - ex; }    // m = f * 2^ex, f in [0.5,1) -> m*2^e in [8192,16384)
+        if (e > 40) e = 40;
+        if (e < -40) e = -40;
+        const float S = ldexpf(1.0f, e);
+        wscale[layer] = S;
+        inv_scale[layer] = 1.0f / (S * kActScale);
+    }
+}
+
+// one thread per 16-byte unit: [k-step][unit: hi ci 0-7, hi ci 8-15, lo ci 0-7, lo ci 8-15][co]
+__global__ void wpack_kernel(const float *__restrict__ blob, PackAux aux, const float *__restrict__ wscale, uint4 *__restrict__ out) {
+    const int64_t total = (int64_t)kG * 512;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i & 127), u = (int)((i >> 7) & 3), g = (int)(i >> 9);
+        int layer, tap, ci0;
+        if (g < kKSteps0) { layer = 0; tap = g; ci0 = 0; }
+        else { const int j = g - kKSteps0; layer = 1 + j / kKStepsL; const int k = j % kKStepsL; tap = k >> 3; ci0 = (k & 7) * 16; }
+        const int cin = aux.cin[layer];
+        const float S = wscale[layer];
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = ci0 + (u & 1) * 8 + e;
+            float w = 0.f;
+            if (ci < cin) w = blob[aux.koff[layer] + ((int64_t)tap * cin + ci) * kC + co] * S;
+            const __half hi = __float2half_rn(w);
+            h[e] = (u & 2) ? __float2half_rn(w - __half2float(hi)) : hi;
+        }
+        out[i] = *reinterpret_cast<const uint4 *>(h);
+    }
+}
+
+}  // namespace ts
+
+int net_ts_prepare(ck_net *net) {
+    const NetLayout L = net_layout();
+    if (!net->d_wts) {
+        // [packed weights][wscale 8 f][inv 8 f][plane5 81 f]
+        CK_CUDA(cudaMalloc(&net->d_wts, ts::kCopies * ts::kWtsBytes + 1024));
+    }
+    float *aux = (float *)((uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes);
+    ts::PackAux h;
+    for (int i = 0; i < 8; ++i) { h.koff[i] = L.conv[i].kernel; h.cin[i] = L.conv[i].cin; }
+    float p5[81];
+    for (int i = 0; i <= 80; ++i) p5[i] = (float)((double)i / 80.0);
+    CK_CUDA(cudaMemcpy(aux + 16, p5, sizeof(p5), cudaMemcpyHostToDevice));
+    ts::wscale_kernel<<<8, 256>>>(net->d_blob, h, aux, aux + 8);
+    ts::wpack_kernel<<<1024, 256>>>(net->d_blob, h, aux, (uint4 *)net->d_wts);
+    CK_CUDA(cudaGetLastError());
+    for (int c = 1; c < ts::kCopies; ++c)
+        CK_CUDA(cudaMemcpyAsync((uint8_t *)net->d_wts + c * ts::kWtsBytes, net->d_wts, ts::kWtsBytes, cudaMemcpyDeviceToDevice, 0));
+    return CK_OK;
+}
+
+template <int kEpiWarps>
+static int launch_tower_ts(ck_net *net, const ts::TowerParams &prm, int64_t max_n, cudaStream_t stream) {
+    static bool attr_done = false;
+    static_assert(ts::kSmem <= 232448, "tower tiles do not fit in shared memory");
+    if (!attr_done) {
+        CK_CUDA(cudaFuncSetAttribute(ts::tower_ts_kernel<kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmem));
+        attr_done = true;
+    }
+    const int64_t pairs = (max_n + 2 * ts::kP - 1) / (2 * ts::kP);
+    const int grid = (int)std::min<int64_t>(pairs, num_sms(net->device));
+    ts::tower_ts_kernel<kEpiWarps><<<grid, (ts::kLoaderWarps + 2 + kEpiWarps) * 32, ts::kSmem, stream>>>(prm);
+    CK_CUDA(cudaGetLastError());
+    return CK_OK;
+}
+
+int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev, float *d_trunk, float *d_pconv,
+                 cudaStream_t stream, int *launches) {
+    if (!net->d_wts) return fail(CK_ERR_NO_NET, "tcgen05 tower: weights were never packed");
+    const NetLayout L = net_layout();
+    const float *aux = (const float *)((const uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes);
+    ts::TowerParams prm;
+    prm.leaves = d_leaves; prm.n_dev = n_dev; prm.max_n = (int32_t)max_n;
+    prm.wts = (const uint4 *)net->d_wts; prm.blob = net->d_blob; prm.fold = net->d_scale;
+    prm.inv_scale = aux + 8;
+    prm.plane5 = aux + 16;
+    for (int i = 0; i < 8; ++i) prm.bias_off[i] = L.conv[i].bias;
+    prm.trunk = d_trunk; prm.pconv = d_pconv;
+    static const int variant = [] { const char *v = getenv("CK_TS_VARIANT"); return v ? atoi(v) : 0; }();
+    const int rc = variant == 1 ? launch_tower_ts<16>(net, prm, max_n, stream) : launch_tower_ts<8>(net, prm, max_n, stream);
+    if (rc != CK_OK) return rc;
+    if (launches) *launches += 1;
+    return CK_OK;
+}
+
+}  // namespace ck
