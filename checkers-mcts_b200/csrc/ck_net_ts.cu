@@ -95,9 +95,8 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
 template <int kEpiWarps>
 __global__ void __launch_bounds__((kLoaderWarps + 2 + kEpiWarps) * 32, 1)
 tower_ts_kernel(const TowerParams prm) {
-    static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
+    static_assert(kEpiWarps == 8, "epilogue: two warps per TMEM lane quadrant, 64 accumulator columns each");
     constexpr int kMmaWarp0 = kLoaderWarps + kEpiWarps;            // warps kMmaWarp0 (tile X) and kMmaWarp0 + 1 (tile Y)
-    constexpr int kRowsPer = 8 / (kEpiWarps / 4);       // board rows (16 accumulator columns each) per epilogue warp
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n = prm.max_n;
@@ -217,8 +216,6 @@ tower_ts_kernel(const TowerParams prm) {
         // warp serves both tiles and takes whichever accumulator is complete first. =====
         const int ew = warp - kLoaderWarps, et = tid - kLoaderWarps * 32;
         const int quad = warp & 3, sub = ew >> 2;
-        const int co = quad * 32 + lane;
-        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
 
         auto build_input = [&](int t, uint32_t k) {
             // planes 0..13 (+2 zero channels) of the tile's positions, thread = (square, chunk, position)
@@ -276,49 +273,49 @@ tower_ts_kernel(const TowerParams prm) {
             const uint32_t k = t ? ek1 : ek0;
             if (t) ph1 ^= 1u; else ph0 ^= 1u;
             tc_fence_after();
-            const float bias = prm.blob[prm.bias_off[layer] + co];
-            const float sc = prm.fold[kScaleTower + layer * 2 * kC + co] * kActScale;
-            const float sh = prm.fold[kScaleTower + layer * 2 * kC + kC + co] * kActScale;
-            const float inv = prm.inv_scale[layer];
-            // accumulator column j = (2*x + p)*8 + y: 16 columns = board row x of both positions
-            uint8_t *abase = smem + t * kTileBytes + (co >> 3) * kChunkStride + (co & 7) * 2;
+            // Accumulator column = (2*x + p)*8 + y: one 8-column group g = 2*x + p is board row x of position p.
+            // Each warp drains 64 columns (8 groups) of its 32 lanes in two 16-lane halves with the
+            // fragment-layout load (thread: lanes t/4 and t/4+8, two adjacent squares), so that
+            // stmatrix.trans can write whole 16-byte units (8 channels of one square) of the next
+            // layer's operand: 8x fewer shared-memory store instructions than 2-byte stores.
             const int64_t pos0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * (2 * kP) + t * kP;
             float *gbase = nullptr;
-            if (layer >= 6) gbase = (layer == 6 ? prm.trunk : prm.pconv) + (pos0 * kC + co) * 64;
-            const uint32_t t_acc = t_lane + (uint32_t)(t * kN);
-            const int x0 = sub * kRowsPer;
-            uint32_t ra[16], rb[16];
-            tmem_ld16_async(t_acc + (uint32_t)(x0 * 16), ra);
+            if (layer >= 6) gbase = (layer == 6 ? prm.trunk : prm.pconv) + pos0 * kC * 64;
+            const float inv = prm.inv_scale[layer];
+            const int t4 = lane >> 2, tq = lane & 3;
+            const float *fold = prm.fold + kScaleTower + layer * 2 * kC;
+            const float *bias_p = prm.blob + prm.bias_off[layer];
+            const uint32_t st_base = smem_u32(smem) + (uint32_t)(t * kTileBytes) + ((lane >> 4) ? (uint32_t)kSplitBytes : 0u) +
+                                     (uint32_t)((4 * quad + ((lane >> 3) & 1)) * kChunkStride + sq_off(0, 1, (lane & 7) + 1));
+            uint32_t cur[32];
 #pragma unroll
-            for (int i = 0; i < kRowsPer; ++i) {
-                uint32_t *cur = (i & 1) ? rb : ra, *nxt = (i & 1) ? ra : rb;
-                tmem_ld_wait16(cur);
-                if (i + 1 < kRowsPer) tmem_ld16_async(t_acc + (uint32_t)((x0 + i + 1) * 16), nxt);
-                const int x = x0 + i;
+            for (int h = 0; h < 2; ++h) {
+                tmem_ld_16x256b_x8_async(((uint32_t)(quad * 32 + 16 * h) << 16) + (uint32_t)(t * kN + 64 * sub), cur);
+                const int ch0 = quad * 32 + 16 * h + t4;                 // and ch0 + 8
+                const float bias0 = bias_p[ch0], bias1 = bias_p[ch0 + 8];
+                const float sc0 = fold[ch0] * kActScale, sc1 = fold[ch0 + 8] * kActScale;
+                const float sh0 = fold[kC + ch0] * kActScale, sh1 = fold[kC + ch0 + 8] * kActScale;
+                tmem_ld_wait32(cur);
 #pragma unroll
-                for (int p = 0; p < kP; ++p) {
-                    float a[8];
-#pragma unroll
-                    for (int y = 0; y < 8; ++y)
-                        a[y] = fmaf(fmaxf(fmaf(__uint_as_float(cur[8 * p + y]), inv, bias), 0.f), sc, sh);
+                for (int j = 0; j < 8; ++j) {
+                    const int g = 8 * sub + j, x = g >> 1, p = g & 1;
+                    const float a0 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 0]), inv, bias0), 0.f), sc0, sh0);
+                    const float a1 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 1]), inv, bias0), 0.f), sc0, sh0);
+                    const float a2 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 2]), inv, bias1), 0.f), sc1, sh1);
+                    const float a3 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 3]), inv, bias1), 0.f), sc1, sh1);
                     if (gbase != nullptr && pos0 + p < n) {
-                        float *gout = gbase + (int64_t)p * kC * 64 + x * 8;
                         constexpr float q = 1.0f / kActScale;
-                        *reinterpret_cast<float4 *>(gout) = make_float4(a[0] * q, a[1] * q, a[2] * q, a[3] * q);
-                        *reinterpret_cast<float4 *>(gout + 4) = make_float4(a[4] * q, a[5] * q, a[6] * q, a[7] * q);
+                        float *gout = gbase + ((int64_t)p * kC + ch0) * 64 + x * 8 + 2 * tq;
+                        *reinterpret_cast<float2 *>(gout) = make_float2(a0 * q, a1 * q);
+                        *reinterpret_cast<float2 *>(gout + 8 * 64) = make_float2(a2 * q, a3 * q);
                     }
                     if (layer < kTowerConvs - 1) {
-                        uint8_t *dst = abase + sq_off(p, x + 1, 1);
-#pragma unroll
-                        for (int y = 0; y < 8; y += 2) {
-                            const __half2 h = __floats2half2_rn(a[y], a[y + 1]);
-                            const float2 f = __half22float2(h);
-                            const __half2 l = __floats2half2_rn(a[y] - f.x, a[y + 1] - f.y);
-                            *reinterpret_cast<__half *>(dst + y * 16) = __low2half(h);
-                            *reinterpret_cast<__half *>(dst + (y + 1) * 16) = __high2half(h);
-                            *reinterpret_cast<__half *>(dst + kSplitBytes + y * 16) = __low2half(l);
-                            *reinterpret_cast<__half *>(dst + kSplitBytes + (y + 1) * 16) = __high2half(l);
-                        }
+                        const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                        const __half2 l0 = __floats2half2_rn(a0 - f0.x, a1 - f0.y), l1 = __floats2half2_rn(a2 - f1.x, a3 - f1.y);
+                        stmatrix_x4_trans(st_base + (uint32_t)(2 * h * kChunkStride + g * 160),
+                                          *reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                                          *reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
                     }
                 }
             }
@@ -438,7 +435,8 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     for (int i = 0; i < 8; ++i) prm.bias_off[i] = L.conv[i].bias;
     prm.trunk = d_trunk; prm.pconv = d_pconv;
     static const int variant = [] { const char *v = getenv("CK_TS_VARIANT"); return v ? atoi(v) : 0; }();
-    const int rc = variant == 1 ? launch_tower_ts<16>(net, prm, max_n, stream) : launch_tower_ts<8>(net, prm, max_n, stream);
+    (void)variant;
+    const int rc = launch_tower_ts<8>(net, prm, max_n, stream);
     if (rc != CK_OK) return rc;
     if (launches) *launches += 1;
     return CK_OK;
