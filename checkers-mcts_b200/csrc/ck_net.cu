@@ -166,16 +166,22 @@ conv3x3_simt_kernel(const ck_leaf *__restrict__ leaves, const float *__restrict_
 }
 
 // ---- heads --------------------------------------------------------------------------------
-// 8 positions per CTA so that the 1 MB policy-dense matrix is read from L2 once per 8
-// positions.  Inputs: trunk = conv6 output, pconv = policy conv3x3 output, fp32 [n][128][64].
-constexpr int kHeadPB = 8;
+// Policy head tail (conv1x1 128->8, ReLU, BN, Flatten over (x,y,c), Dense 512->512, softmax;
+// training_pipeline.py:89-100) and value head (conv1x1 128->1, ReLU, BN, Dense 64 ReLU BN, Dense 1
+// tanh; :102-112) in fp32 on the CUDA cores.  kHeadPB = 32 positions per CTA: the 1 MB dense matrix
+// is the dominant traffic (L2 -> SM), read once per 32 positions (134 MB per 4096-position batch;
+// at 8 positions per CTA it was 537 MB and the kernel was L2-bandwidth bound).
+// Inputs: trunk = conv6 output, pconv = policy conv3x3 output, fp32 [n][128][64].
+constexpr int kHeadPB = 32;
+constexpr int kHeadThreads = 512;
+constexpr int kHeadSmem = (512 * kHeadPB + 128 * 8 + kHeadPB * 64) * (int)sizeof(float);
 
 struct HeadParams {
     int64_t pol1x1_k, pol1x1_b, pol_dense_k, pol_dense_b;
     int64_t val1x1_k, val1x1_b, val_d1_k, val_d1_b, val_d2_k, val_d2_b;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kHeadThreads, 1)
 heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, int64_t max_n,
              const int32_t *__restrict__ n_dev, const float *__restrict__ blob, const float *__restrict__ fold,
              HeadParams hp, float *__restrict__ policy, float *__restrict__ value) {
@@ -184,29 +190,34 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
     const int64_t base = (int64_t)blockIdx.x * kHeadPB;
     if (base >= n) return;
     const int npos = (int)min((int64_t)kHeadPB, n - base);
-    __shared__ __align__(16) float s_flat[512 * kHeadPB];   // [i][p] during the dense, [p][512] for softmax
-    __shared__ float s_wp[128 * 8];
-    __shared__ float s_v1[kHeadPB][64];
+    extern __shared__ __align__(16) float s_head[];
+    float *s_flat = s_head;                         // [i][p] during the dense, [p][512] for the softmax
+    float *s_wp = s_head + 512 * kHeadPB;           // policy conv1x1 kernel [c][o]
+    float *s_v1 = s_wp + 128 * 8;                   // value conv1x1 output [p][64]
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    for (int i = tid; i < 128 * 8; i += 256) s_wp[i] = blob[hp.pol1x1_k + i];
+    for (int i = tid; i < 128 * 8; i += kHeadThreads) s_wp[i] = blob[hp.pol1x1_k + i];
     __syncthreads();
-    // policy conv1x1 128 -> 8, ReLU, BN; flatten in (x, y, c) order
-    {
-        const int p = wp;
-        float acc[2][8];
+    // conv1x1 of both heads: one warp per position (two rounds), lanes over squares
+    for (int p = wp; p < kHeadPB; p += kHeadThreads / 32) {
+        float acc[2][8], va0 = 0.f, va1 = 0.f;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int o = 0; o < 8; ++o) acc[h][o] = 0.f;
         if (p < npos) {
             const float *src = pconv + (base + p) * kC * 64;
+            const float *tsrc = trunk + (base + p) * kC * 64;
+#pragma unroll 8
             for (int c = 0; c < kC; ++c) {
                 const float a0 = src[c * 64 + lane], a1 = src[c * 64 + 32 + lane];
+                const float wv = blob[hp.val1x1_k + c];
+                va0 = fmaf(tsrc[c * 64 + lane], wv, va0);
+                va1 = fmaf(tsrc[c * 64 + 32 + lane], wv, va1);
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
-                    const float wv = s_wp[c * 8 + o];
-                    acc[0][o] = fmaf(a0, wv, acc[0][o]);
-                    acc[1][o] = fmaf(a1, wv, acc[1][o]);
+                    const float w = s_wp[c * 8 + o];
+                    acc[0][o] = fmaf(a0, w, acc[0][o]);
+                    acc[1][o] = fmaf(a1, w, acc[1][o]);
                 }
             }
         }
@@ -215,39 +226,44 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
                 const float v = fmaf(fmaxf(acc[h][o] + blob[hp.pol1x1_b + o], 0.f), fold[kScalePol1x1 + o], fold[kScalePol1x1 + 8 + o]);
-                s_flat[((h * 32 + lane) * 8 + o) * kHeadPB + p] = (p < npos) ? v : 0.f;
+                s_flat[((h * 32 + lane) * 8 + o) * kHeadPB + p] = (p < npos) ? v : 0.f;       // flatten in (x, y, c) order
             }
+        const float b = blob[hp.val1x1_b], sc = fold[kScaleVal1x1], sh = fold[kScaleVal1x1 + 1];
+        s_v1[p * 64 + lane] = fmaf(fmaxf(va0 + b, 0.f), sc, sh);
+        s_v1[p * 64 + lane + 32] = fmaf(fmaxf(va1 + b, 0.f), sc, sh);
     }
     __syncthreads();
-    // policy dense 512 -> 512 (Keras kernel [in, out]): thread owns outputs tid and tid+256
-    float l0[kHeadPB], l1[kHeadPB];
-#pragma unroll
-    for (int p = 0; p < kHeadPB; ++p) { l0[p] = 0.f; l1[p] = 0.f; }
+    // policy dense 512 -> 512 (Keras kernel [in, out]): thread = outputs (o, o + 256) x 16 positions
     {
+        const int o = tid & 255, pg = (tid >> 8) * 16;
+        float l0[16], l1[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) { l0[p] = 0.f; l1[p] = 0.f; }
         const float *wd = blob + hp.pol_dense_k;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < 512; ++i) {
-            const float w0 = __ldg(wd + i * 512 + tid), w1 = __ldg(wd + i * 512 + 256 + tid);
-            const float4 fa = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadPB]);
-            const float4 fb = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadPB + 4]);
-            const float f[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+            const float w0 = __ldg(wd + i * 512 + o), w1 = __ldg(wd + i * 512 + 256 + o);
+            float f[16];
 #pragma unroll
-            for (int p = 0; p < kHeadPB; ++p) { l0[p] = fmaf(f[p], w0, l0[p]); l1[p] = fmaf(f[p], w1, l1[p]); }
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadPB + pg + 4 * q]);
+                f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int p = 0; p < 16; ++p) { l0[p] = fmaf(f[p], w0, l0[p]); l1[p] = fmaf(f[p], w1, l1[p]); }
+        }
+        __syncthreads();
+        const float b0 = blob[hp.pol_dense_b + o], b1 = blob[hp.pol_dense_b + 256 + o];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            s_flat[(pg + p) * 512 + o] = l0[p] + b0;
+            s_flat[(pg + p) * 512 + 256 + o] = l1[p] + b1;
         }
     }
     __syncthreads();
-    {
-        const float b0 = blob[hp.pol_dense_b + tid], b1 = blob[hp.pol_dense_b + 256 + tid];
-#pragma unroll
-        for (int p = 0; p < kHeadPB; ++p) {
-            s_flat[p * 512 + tid] = l0[p] + b0;
-            s_flat[p * 512 + 256 + tid] = l1[p] + b1;
-        }
-    }
-    __syncthreads();
-    // softmax, one warp per position
-    if (wp < npos) {
-        float *row = s_flat + wp * 512;
+    for (int p = wp; p < npos; p += kHeadThreads / 32) {
+        // softmax, one warp per position
+        float *row = s_flat + p * 512;
         float m = -INFINITY;
         for (int i = lane; i < 512; i += 32) m = fmaxf(m, row[i]);
 #pragma unroll
@@ -257,45 +273,22 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
         for (int i = 0; i < 16; ++i) { e[i] = expf(row[lane + 32 * i] - m); s += e[i]; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        float *dst = policy + (base + wp) * CK_POLICY_SIZE;
+        float *dst = policy + (base + p) * CK_POLICY_SIZE;
 #pragma unroll
         for (int i = 0; i < 16; ++i) dst[lane + 32 * i] = e[i] / s;
-    }
-    // value head: conv1x1 128 -> 1, ReLU, BN
-    {
-        const int p = wp;
-        if (p < npos) {
-            const float *src = trunk + (base + p) * kC * 64;
-            float a0 = 0.f, a1 = 0.f;
-            for (int c = 0; c < kC; ++c) {
-                const float wv = blob[hp.val1x1_k + c];
-                a0 = fmaf(src[c * 64 + lane], wv, a0);
-                a1 = fmaf(src[c * 64 + 32 + lane], wv, a1);
-            }
-            const float b = blob[hp.val1x1_b], sc = fold[kScaleVal1x1], sh = fold[kScaleVal1x1 + 1];
-            s_v1[p][lane] = fmaf(fmaxf(a0 + b, 0.f), sc, sh);
-            s_v1[p][lane + 32] = fmaf(fmaxf(a1 + b, 0.f), sc, sh);
+        // value head: dense 64 -> 64, ReLU, BN; dense 64 -> 1, tanh
+        float h0 = 0.f, h1 = 0.f;
+        for (int q = 0; q < 64; ++q) {
+            const float v = s_v1[p * 64 + q];
+            h0 = fmaf(v, blob[hp.val_d1_k + q * 64 + lane], h0);
+            h1 = fmaf(v, blob[hp.val_d1_k + q * 64 + 32 + lane], h1);
         }
-    }
-    __syncwarp();
-    {
-        const int p = wp;
-        if (p < npos) {
-            // dense 64 -> 64, ReLU, BN
-            float h0 = 0.f, h1 = 0.f;
-            for (int s = 0; s < 64; ++s) {
-                const float v = s_v1[p][s];
-                h0 = fmaf(v, blob[hp.val_d1_k + s * 64 + lane], h0);
-                h1 = fmaf(v, blob[hp.val_d1_k + s * 64 + 32 + lane], h1);
-            }
-            h0 = fmaf(fmaxf(h0 + blob[hp.val_d1_b + lane], 0.f), fold[kScaleValD1 + lane], fold[kScaleValD1 + 64 + lane]);
-            h1 = fmaf(fmaxf(h1 + blob[hp.val_d1_b + 32 + lane], 0.f), fold[kScaleValD1 + 32 + lane], fold[kScaleValD1 + 96 + lane]);
-            // dense 64 -> 1, tanh
-            float t = h0 * blob[hp.val_d2_k + lane] + h1 * blob[hp.val_d2_k + 32 + lane];
+        h0 = fmaf(fmaxf(h0 + blob[hp.val_d1_b + lane], 0.f), fold[kScaleValD1 + lane], fold[kScaleValD1 + 64 + lane]);
+        h1 = fmaf(fmaxf(h1 + blob[hp.val_d1_b + 32 + lane], 0.f), fold[kScaleValD1 + 32 + lane], fold[kScaleValD1 + 96 + lane]);
+        float t = h0 * blob[hp.val_d2_k + lane] + h1 * blob[hp.val_d2_k + 32 + lane];
 #pragma unroll
-            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
-            if (lane == 0) value[base + p] = tanhf(t + blob[hp.val_d2_b]);
-        }
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+        if (lane == 0) value[base + p] = tanhf(t + blob[hp.val_d2_b]);
     }
 }
 
@@ -381,7 +374,12 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
     if (net->ev_after_tower) CK_CUDA(cudaEventRecord(net->ev_after_tower, stream));
     HeadParams hp{L.pol1x1.kernel, L.pol1x1.bias, L.pol_dense_k, L.pol_dense_b, L.val1x1.kernel, L.val1x1.bias,
                   L.val_d1_k, L.val_d1_b, L.val_d2_k, L.val_d2_b};
-    heads_kernel<<<(unsigned)((max_n + kHeadPB - 1) / kHeadPB), 256, 0, stream>>>(
+    static bool heads_attr_done = false;
+    if (!heads_attr_done) {
+        CK_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+        heads_attr_done = true;
+    }
+    heads_kernel<<<(unsigned)((max_n + kHeadPB - 1) / kHeadPB), kHeadThreads, kHeadSmem, stream>>>(
         trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
     ++nl;
     CK_CUDA(cudaGetLastError());
