@@ -173,14 +173,18 @@ conv3x3_simt_kernel(const ck_leaf *__restrict__ leaves, const float *__restrict_
 // at 8 positions per CTA it was 537 MB and the kernel was L2-bandwidth bound).
 // Inputs: trunk = conv6 output, pconv = policy conv3x3 output, fp32 [n][128][64].
 constexpr int kHeadPB = 32;
+constexpr int kHeadStride = kHeadPB + 4;            // row stride of s_flat[i][p]: float4-aligned, spreads banks
 constexpr int kHeadThreads = 512;
-constexpr int kHeadSmem = (512 * kHeadPB + 128 * 8 + kHeadPB * 64) * (int)sizeof(float);
+constexpr int kHeadSmem = (512 * kHeadStride + 128 * 8 + kHeadPB * 64) * (int)sizeof(float);
 
 struct HeadParams {
     int64_t pol1x1_k, pol1x1_b, pol_dense_k, pol_dense_b;
     int64_t val1x1_k, val1x1_b, val_d1_k, val_d1_b, val_d2_k, val_d2_b;
 };
 
+// kFused: the tower already applied both conv1x1 (ck_net_ts.cu); `trunk` then holds the value conv output
+// [n][64] and `pconv` the flattened policy features [n][512].
+template <bool kFused>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, int64_t max_n,
              const int32_t *__restrict__ n_dev, const float *__restrict__ blob, const float *__restrict__ fold,
@@ -192,45 +196,53 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
     const int npos = (int)min((int64_t)kHeadPB, n - base);
     extern __shared__ __align__(16) float s_head[];
     float *s_flat = s_head;                         // [i][p] during the dense, [p][512] for the softmax
-    float *s_wp = s_head + 512 * kHeadPB;           // policy conv1x1 kernel [c][o]
+    float *s_wp = s_head + 512 * kHeadStride;       // policy conv1x1 kernel [c][o]
     float *s_v1 = s_wp + 128 * 8;                   // value conv1x1 output [p][64]
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    for (int i = tid; i < 128 * 8; i += kHeadThreads) s_wp[i] = blob[hp.pol1x1_k + i];
-    __syncthreads();
-    // conv1x1 of both heads: one warp per position (two rounds), lanes over squares
-    for (int p = wp; p < kHeadPB; p += kHeadThreads / 32) {
-        float acc[2][8], va0 = 0.f, va1 = 0.f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int o = 0; o < 8; ++o) acc[h][o] = 0.f;
-        if (p < npos) {
-            const float *src = pconv + (base + p) * kC * 64;
-            const float *tsrc = trunk + (base + p) * kC * 64;
-#pragma unroll 8
-            for (int c = 0; c < kC; ++c) {
-                const float a0 = src[c * 64 + lane], a1 = src[c * 64 + 32 + lane];
-                const float wv = blob[hp.val1x1_k + c];
-                va0 = fmaf(tsrc[c * 64 + lane], wv, va0);
-                va1 = fmaf(tsrc[c * 64 + 32 + lane], wv, va1);
-#pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    const float w = s_wp[c * 8 + o];
-                    acc[0][o] = fmaf(a0, w, acc[0][o]);
-                    acc[1][o] = fmaf(a1, w, acc[1][o]);
+    if (kFused) {
+        for (int idx = tid; idx < kHeadPB * 512; idx += kHeadThreads) {
+            const int p = idx >> 9, i = idx & 511;
+            s_flat[i * kHeadStride + p] = p < npos ? pconv[(base + p) * 512 + i] : 0.f;
+        }
+        for (int idx = tid; idx < kHeadPB * 64; idx += kHeadThreads) s_v1[idx] = (idx >> 6) < npos ? trunk[base * 64 + idx] : 0.f;
+    } else {
+        for (int i = tid; i < 128 * 8; i += kHeadThreads) s_wp[i] = blob[hp.pol1x1_k + i];
+        __syncthreads();
+        // conv1x1 of both heads: one warp per position (two rounds), lanes over squares
+        for (int p = wp; p < kHeadPB; p += kHeadThreads / 32) {
+            float acc[2][8], va0 = 0.f, va1 = 0.f;
+    #pragma unroll
+            for (int h = 0; h < 2; ++h)
+    #pragma unroll
+                for (int o = 0; o < 8; ++o) acc[h][o] = 0.f;
+            if (p < npos) {
+                const float *src = pconv + (base + p) * kC * 64;
+                const float *tsrc = trunk + (base + p) * kC * 64;
+    #pragma unroll 8
+                for (int c = 0; c < kC; ++c) {
+                    const float a0 = src[c * 64 + lane], a1 = src[c * 64 + 32 + lane];
+                    const float wv = blob[hp.val1x1_k + c];
+                    va0 = fmaf(tsrc[c * 64 + lane], wv, va0);
+                    va1 = fmaf(tsrc[c * 64 + 32 + lane], wv, va1);
+    #pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const float w = s_wp[c * 8 + o];
+                        acc[0][o] = fmaf(a0, w, acc[0][o]);
+                        acc[1][o] = fmaf(a1, w, acc[1][o]);
+                    }
                 }
             }
+    #pragma unroll
+            for (int h = 0; h < 2; ++h)
+    #pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const float v = fmaf(fmaxf(acc[h][o] + blob[hp.pol1x1_b + o], 0.f), fold[kScalePol1x1 + o], fold[kScalePol1x1 + 8 + o]);
+                    s_flat[((h * 32 + lane) * 8 + o) * kHeadStride + p] = (p < npos) ? v : 0.f;       // flatten in (x, y, c) order
+                }
+            const float b = blob[hp.val1x1_b], sc = fold[kScaleVal1x1], sh = fold[kScaleVal1x1 + 1];
+            s_v1[p * 64 + lane] = fmaf(fmaxf(va0 + b, 0.f), sc, sh);
+            s_v1[p * 64 + lane + 32] = fmaf(fmaxf(va1 + b, 0.f), sc, sh);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const float v = fmaf(fmaxf(acc[h][o] + blob[hp.pol1x1_b + o], 0.f), fold[kScalePol1x1 + o], fold[kScalePol1x1 + 8 + o]);
-                s_flat[((h * 32 + lane) * 8 + o) * kHeadPB + p] = (p < npos) ? v : 0.f;       // flatten in (x, y, c) order
-            }
-        const float b = blob[hp.val1x1_b], sc = fold[kScaleVal1x1], sh = fold[kScaleVal1x1 + 1];
-        s_v1[p * 64 + lane] = fmaf(fmaxf(va0 + b, 0.f), sc, sh);
-        s_v1[p * 64 + lane + 32] = fmaf(fmaxf(va1 + b, 0.f), sc, sh);
     }
     __syncthreads();
     // policy dense 512 -> 512 (Keras kernel [in, out]): thread = outputs (o, o + 256) x 16 positions
@@ -246,7 +258,7 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
             float f[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 v = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadPB + pg + 4 * q]);
+                const float4 v = *reinterpret_cast<const float4 *>(&s_flat[i * kHeadStride + pg + 4 * q]);
                 f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
             }
 #pragma unroll
@@ -345,6 +357,7 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
     const float *blob = net->d_blob;
     float *trunk = net->d_act0, *pconv = net->d_act1;
     int nl = 0;
+    bool fused = false;
     if (net->impl == CK_NET_IMPL_SIMT) {
         static bool attr_done = false;
         const int smem128 = kC * kPlaneStride * sizeof(float), smem14 = 14 * kPlaneStride * sizeof(float);
@@ -367,8 +380,10 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
     } else {
         // CK_TOWER=ss selects the earlier all-shared-memory tcgen05 kernel (cross-check)
         static const bool use_ss = [] { const char *v = getenv("CK_TOWER"); return v && v[0] == 's'; }();
+        fused = !use_ss;
+        // fused path: d_act0 receives the value conv1x1 output [n][64], d_act1 the policy features [n][512]
         rc = use_ss ? net_tc_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl)
-                    : net_ts_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl);
+                    : net_ts_tower(net, d_leaves, max_n, n_dev, pconv, trunk, stream, &nl);
         if (rc != CK_OK) return rc;
     }
     if (net->ev_after_tower) CK_CUDA(cudaEventRecord(net->ev_after_tower, stream));
@@ -376,11 +391,15 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
                   L.val_d1_k, L.val_d1_b, L.val_d2_k, L.val_d2_b};
     static bool heads_attr_done = false;
     if (!heads_attr_done) {
-        CK_CUDA(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+        CK_CUDA(cudaFuncSetAttribute(heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+        CK_CUDA(cudaFuncSetAttribute(heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
         heads_attr_done = true;
     }
-    heads_kernel<<<(unsigned)((max_n + kHeadPB - 1) / kHeadPB), kHeadThreads, kHeadSmem, stream>>>(
-        trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
+    const unsigned hgrid = (unsigned)((max_n + kHeadPB - 1) / kHeadPB);
+    if (fused)
+        heads_kernel<true><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
+    else
+        heads_kernel<false><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
     ++nl;
     CK_CUDA(cudaGetLastError());
     if (launches) *launches += nl;

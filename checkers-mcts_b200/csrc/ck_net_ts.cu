@@ -42,7 +42,9 @@ constexpr int kChunkStride = kP * 1600 + 16;        // 8 channels x (kP x 100 pa
 constexpr int kSplitBytes = 16 * kChunkStride;      // all 128 channels, hi or lo
 constexpr int kTileBytes = 2 * kSplitBytes;
 constexpr int kKSteps0 = 9, kKStepsL = 72;          // k-steps (16 input channels of one tap) per layer
-constexpr int kG = kKSteps0 + 7 * kKStepsL;         // 513 k-steps = the whole weight stream
+constexpr int kKSteps8 = 8;                          // "layer 8": the policy head's 1x1 conv 128 -> 8, centre tap only
+constexpr int kLayers = kTowerConvs + 1;            // 8 3x3 convolutions + the fused policy conv1x1
+constexpr int kG = kKSteps0 + 7 * kKStepsL + kKSteps8;   // 521 k-steps = the whole weight stream
 constexpr int kNS = 16;                             // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
 constexpr int kLoaderWarps = 8;                     // two sets of four (one warp per TMEM lane quadrant)
@@ -55,7 +57,8 @@ constexpr size_t kWtsBytes = (size_t)kG * 8192;     // [k-step][unit 4][co 128][
 constexpr int kCopies = 8;
 constexpr uint32_t kIdesc = make_idesc_f16(128, kN);
 constexpr int kBarOff = 2 * kTileBytes;
-constexpr int kSmem = kBarOff + 512;
+constexpr int kVredOff = kBarOff + 512;               // value conv1x1 partial sums [tile 2][quadrant 4][128 columns] fp32
+constexpr int kSmem = kVredOff + 2 * 4 * kN * 4 + 16;       // + the two arrival counters
 
 __host__ __device__ constexpr int sq_off(int p, int r, int c) { return ((kP * r + p) * 10 + c) * 16; }
 
@@ -66,23 +69,12 @@ struct TowerParams {
     const uint4 *wts;            // split-fp16 weights, k-step order
     const float *blob;           // Keras-ordered fp32 parameters (biases)
     const float *fold;           // folded BN scale/shift table
-    const float *inv_scale;      // per layer 1 / (weight scale * activation scale)
-    int64_t bias_off[8];
-    float *trunk, *pconv;        // fp32 [n][128][64]
+    const float *inv_scale;      // per layer 1 / (weight scale * activation scale), 9 entries
+    int64_t bias_off[9];         // conv0..6, policy conv3x3, policy conv1x1
+    int64_t val1x1_k, val1x1_b;  // value head conv1x1 128 -> 1 (fp32, reduced in the conv6 epilogue)
+    float *pflat;                // fp32 [n][512]: policy conv1x1 + ReLU + BN, flattened in (x, y, c) order
+    float *vconv;                // fp32 [n][64]: value conv1x1 + ReLU + BN
     const float *plane5;         // 81-entry float32(n/80) table
-};
-
-// position of a tile in the weight stream
-struct Cursor {
-    int layer = 0, k = 0;
-    __device__ __forceinline__ int len() const { return layer == 0 ? kKSteps0 : kKStepsL; }
-    __device__ __forceinline__ bool first() const { return k == 0; }
-    __device__ __forceinline__ bool last() const { return k == len() - 1; }
-    __device__ __forceinline__ int tap() const { return layer == 0 ? k : (k >> 3); }
-    __device__ __forceinline__ int chunk0() const { return layer == 0 ? 0 : ((k & 7) << 1); }
-    __device__ __forceinline__ void advance() {
-        if (++k == len()) { k = 0; layer = layer == kTowerConvs - 1 ? 0 : layer + 1; }
-    }
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
@@ -119,6 +111,8 @@ tower_ts_kernel(const TowerParams prm) {
             for (int s = 0; s < kNS; ++s) { mbar_init(bar_full(s), 4); mbar_init(bar_empty(s), 2); }
             for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 32 * kEpiWarps); }
             mbar_init_fence();
+            reinterpret_cast<int *>(smem + kVredOff + 2 * 4 * kN * 4)[0] = 0;
+            reinterpret_cast<int *>(smem + kVredOff + 2 * 4 * kN * 4)[1] = 0;
         }
         __syncwarp();
         tmem_alloc<512>(smem_u32(s_tmem));
@@ -188,24 +182,23 @@ tower_ts_kernel(const TowerParams prm) {
         uint32_t s = 0, ar_phase = 0;
         for (uint32_t pair = 0; pair < npu; ++pair) {
             if (pair >= np) break;
-            for (int layer = 0; layer < kTowerConvs; ++layer) {
+            for (int layer = 0; layer < kLayers; ++layer) {
                 mbar_wait(bar_act_ready(t), ar_phase); ar_phase ^= 1u;
                 tc_fence_after();
                 const int nk = layer == 0 ? 1 : 8;
+                const int tap_lo = layer == kLayers - 1 ? 4 : 0, tap_hi = layer == kLayers - 1 ? 5 : 9;   // conv1x1 = centre tap
                 uint32_t acc = 0u;
-                for (int tr = 0; tr < 3; ++tr) {
-                    for (int tcl = 0; tcl < 3; ++tcl) {
-                        uint32_t b = tile16 + (uint32_t)(kP * tr * 10 + tcl);           // sq_off(0, tr, tcl) / 16
+                for (int tap = tap_lo; tap < tap_hi; ++tap) {
+                    uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);     // sq_off(0, tap / 3, tap % 3) / 16
 #pragma unroll 1
-                        for (int kc = 0; kc < nk; ++kc, ++s) {
-                            const uint32_t slot = s & (kNS - 1);
-                            mbar_wait(bar_full(slot), (s >> 4) & 1u);
-                            tc_fence_after();
-                            tc_kstep_ts_elect(d, kWCol0 + slot * 16, kDescHi | (uint64_t)(kDescLo + b), (uint32_t)(kSplitBytes >> 4), kIdesc, acc,
-                                              bar_empty(slot));            // 2 arrivals (X and Y) free the slot
-                            acc = 1u;
-                            b += (uint32_t)(2 * kChunkStride) >> 4;
-                        }
+                    for (int kc = 0; kc < nk; ++kc, ++s) {
+                        const uint32_t slot = s & (kNS - 1);
+                        mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                        tc_fence_after();
+                        tc_kstep_ts_elect(d, kWCol0 + slot * 16, kDescHi | (uint64_t)(kDescLo + b), (uint32_t)(kSplitBytes >> 4), kIdesc, acc,
+                                          bar_empty(slot));            // 2 arrivals (X and Y) free the slot
+                        acc = 1u;
+                        b += (uint32_t)(2 * kChunkStride) >> 4;
                     }
                 }
                 tc_commit_elect(bar_acc_full(t));
@@ -279,37 +272,38 @@ tower_ts_kernel(const TowerParams prm) {
             // stmatrix.trans can write whole 16-byte units (8 channels of one square) of the next
             // layer's operand: 8x fewer shared-memory store instructions than 2-byte stores.
             const int64_t pos0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * (2 * kP) + t * kP;
-            float *gbase = nullptr;
-            if (layer >= 6) gbase = (layer == 6 ? prm.trunk : prm.pconv) + pos0 * kC * 64;
             const float inv = prm.inv_scale[layer];
             const int t4 = lane >> 2, tq = lane & 3;
-            const float *fold = prm.fold + kScaleTower + layer * 2 * kC;
-            const float *bias_p = prm.blob + prm.bias_off[layer];
-            const uint32_t st_base = smem_u32(smem) + (uint32_t)(t * kTileBytes) + ((lane >> 4) ? (uint32_t)kSplitBytes : 0u) +
-                                     (uint32_t)((4 * quad + ((lane >> 3) & 1)) * kChunkStride + sq_off(0, 1, (lane & 7) + 1));
             uint32_t cur[32];
+            if (layer < kTowerConvs) {
+                const float *fold = prm.fold + kScaleTower + layer * 2 * kC;
+                const float *bias_p = prm.blob + prm.bias_off[layer];
+                const uint32_t st_base = smem_u32(smem) + (uint32_t)(t * kTileBytes) + ((lane >> 4) ? (uint32_t)kSplitBytes : 0u) +
+                                         (uint32_t)((4 * quad + ((lane >> 3) & 1)) * kChunkStride + sq_off(0, 1, (lane & 7) + 1));
+                float vp[16];                                   // value conv1x1 partial sums (conv6 epilogue only)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                tmem_ld_16x256b_x8_async(((uint32_t)(quad * 32 + 16 * h) << 16) + (uint32_t)(t * kN + 64 * sub), cur);
-                const int ch0 = quad * 32 + 16 * h + t4;                 // and ch0 + 8
-                const float bias0 = bias_p[ch0], bias1 = bias_p[ch0 + 8];
-                const float sc0 = fold[ch0] * kActScale, sc1 = fold[ch0 + 8] * kActScale;
-                const float sh0 = fold[kC + ch0] * kActScale, sh1 = fold[kC + ch0 + 8] * kActScale;
-                tmem_ld_wait32(cur);
+                for (int i = 0; i < 16; ++i) vp[i] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int g = 8 * sub + j, x = g >> 1, p = g & 1;
-                    const float a0 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 0]), inv, bias0), 0.f), sc0, sh0);
-                    const float a1 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 1]), inv, bias0), 0.f), sc0, sh0);
-                    const float a2 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 2]), inv, bias1), 0.f), sc1, sh1);
-                    const float a3 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 3]), inv, bias1), 0.f), sc1, sh1);
-                    if (gbase != nullptr && pos0 + p < n) {
-                        constexpr float q = 1.0f / kActScale;
-                        float *gout = gbase + ((int64_t)p * kC + ch0) * 64 + x * 8 + 2 * tq;
-                        *reinterpret_cast<float2 *>(gout) = make_float2(a0 * q, a1 * q);
-                        *reinterpret_cast<float2 *>(gout + 8 * 64) = make_float2(a2 * q, a3 * q);
-                    }
-                    if (layer < kTowerConvs - 1) {
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld_16x256b_x8_async(((uint32_t)(quad * 32 + 16 * h) << 16) + (uint32_t)(t * kN + 64 * sub), cur);
+                    const int ch0 = quad * 32 + 16 * h + t4;                 // and ch0 + 8
+                    const float bias0 = bias_p[ch0], bias1 = bias_p[ch0 + 8];
+                    const float sc0 = fold[ch0] * kActScale, sc1 = fold[ch0 + 8] * kActScale;
+                    const float sh0 = fold[kC + ch0] * kActScale, sh1 = fold[kC + ch0 + 8] * kActScale;
+                    float wv0 = 0.f, wv1 = 0.f;
+                    if (layer == 6) { wv0 = prm.blob[prm.val1x1_k + ch0]; wv1 = prm.blob[prm.val1x1_k + ch0 + 8]; }
+                    tmem_ld_wait32(cur);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int g = 8 * sub + j;
+                        const float a0 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 0]), inv, bias0), 0.f), sc0, sh0);
+                        const float a1 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 1]), inv, bias0), 0.f), sc0, sh0);
+                        const float a2 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 2]), inv, bias1), 0.f), sc1, sh1);
+                        const float a3 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 3]), inv, bias1), 0.f), sc1, sh1);
+                        if (layer == 6) {
+                            vp[2 * j] = fmaf(wv1, a2, fmaf(wv0, a0, vp[2 * j]));
+                            vp[2 * j + 1] = fmaf(wv1, a3, fmaf(wv0, a1, vp[2 * j + 1]));
+                        }
                         const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
                         const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
                         const __half2 l0 = __floats2half2_rn(a0 - f0.x, a1 - f0.y), l1 = __floats2half2_rn(a2 - f1.x, a3 - f1.y);
@@ -318,13 +312,62 @@ tower_ts_kernel(const TowerParams prm) {
                                           *reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
                     }
                 }
-            }
-            if (layer < kTowerConvs - 1) {
+                if (layer == 6) {
+                    // value head conv1x1 128 -> 1 (training_pipeline.py:102-105) on the conv6 output while it is in
+                    // registers: reduce over the 8 lanes that hold different channels, park the per-quadrant
+                    // partial sums in shared memory; the LAST of the 8 warps to get here adds the four
+                    // quadrants in a fixed order and writes ReLU/BN'd results (deterministic, no barrier).
+                    float *vred = reinterpret_cast<float *>(smem + kVredOff) + (t * 4 + quad) * kN + 64 * sub;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = vp[i];
+                        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                        v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+                        v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+                        if (t4 == 0) vred[8 * (i >> 1) + 2 * tq + (i & 1)] = v;
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    int *vcnt = reinterpret_cast<int *>(smem + kVredOff + 2 * 4 * kN * 4) + t;
+                    int old = 0;
+                    if (lane == 0) old = atomicAdd(vcnt, 1);
+                    old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                    if (old == kEpiWarps - 1) {
+                        if (lane == 0) *vcnt = 0;
+                        __threadfence_block();
+                        const float *vr = reinterpret_cast<const float *>(smem + kVredOff) + t * 4 * kN;
+                        const float bv = prm.blob[prm.val1x1_b], scv = prm.fold[kScaleVal1x1], shv = prm.fold[kScaleVal1x1 + 1];
+                        constexpr float q = 1.0f / kActScale;
+                        for (int col = lane; col < kN; col += 32) {
+                            const float sum = ((vr[col] + vr[kN + col]) + vr[2 * kN + col]) + vr[3 * kN + col];
+                            const int g = col >> 3, x = g >> 1, p = g & 1, y = col & 7;
+                            if (pos0 + p < n) prm.vconv[(pos0 + p) * 64 + x * 8 + y] = fmaf(fmaxf(fmaf(sum, q, bv), 0.f), scv, shv);
+                        }
+                    }
+                }
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar_act_ready(t));
                 if (t) el1 = layer + 1; else el0 = layer + 1;
             } else {
+                // fused policy conv1x1 128 -> 8 (+ bias, ReLU, BN; training_pipeline.py:89-96): accumulator rows 0..7,
+                // i.e. the first 16-lane half of quadrant 0; flattened in (x, y, c) order for the Dense(512)
+                if (quad == 0) {
+                    tmem_ld_16x256b_x8_async((uint32_t)(t * kN + 64 * sub), cur);
+                    const int o = t4;
+                    const float bias0 = prm.blob[prm.bias_off[8] + o];
+                    const float sc0 = prm.fold[kScalePol1x1 + o], sh0 = prm.fold[kScalePol1x1 + 8 + o];
+                    tmem_ld_wait32(cur);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int g = 8 * sub + j, x = g >> 1, p = g & 1;
+                        if (pos0 + p < n) {
+                            float *dst = prm.pflat + (pos0 + p) * 512 + (x * 8 + 2 * tq) * 8 + o;
+                            dst[0] = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 0]), inv, bias0), 0.f), sc0, sh0);
+                            dst[8] = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 1]), inv, bias0), 0.f), sc0, sh0);
+                        }
+                    }
+                }
                 tc_fence_before();
                 if (t) { el1 = 0; ek1 = k + 1; } else { el0 = 0; ek0 = k + 1; }
                 if (k + 1 < np) build_input(t, k + 1);
@@ -337,12 +380,12 @@ tower_ts_kernel(const TowerParams prm) {
 }
 
 // ---- weight packing (once per ck_net_set_weights) ---------------------------------------------
-struct PackAux { int64_t koff[8]; int cin[8]; };
+struct PackAux { int64_t koff[9]; int cin[9]; };     // conv0..6, policy conv3x3, policy conv1x1 (128 -> 8)
 
 // per layer: power-of-two scale S with max|w| * S in [8192, 16384)
 __global__ void wscale_kernel(const float *__restrict__ blob, PackAux aux, float *__restrict__ wscale, float *__restrict__ inv_scale) {
     const int layer = blockIdx.x;
-    const int64_t n = (int64_t)9 * aux.cin[layer] * kC;
+    const int64_t n = layer < kTowerConvs ? (int64_t)9 * aux.cin[layer] * kC : (int64_t)kC * 8;
     const float *w = blob + aux.koff[layer];
     float m = 0.f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
@@ -369,15 +412,17 @@ __global__ void wpack_kernel(const float *__restrict__ blob, PackAux aux, const 
         const int co = (int)(i & 127), u = (int)((i >> 7) & 3), g = (int)(i >> 9);
         int layer, tap, ci0;
         if (g < kKSteps0) { layer = 0; tap = g; ci0 = 0; }
-        else { const int j = g - kKSteps0; layer = 1 + j / kKStepsL; const int k = j % kKStepsL; tap = k >> 3; ci0 = (k & 7) * 16; }
+        else if (g < kKSteps0 + 7 * kKStepsL) { const int j = g - kKSteps0; layer = 1 + j / kKStepsL; const int k = j % kKStepsL; tap = k >> 3; ci0 = (k & 7) * 16; }
+        else { layer = kTowerConvs; tap = 0; ci0 = (g - kKSteps0 - 7 * kKStepsL) * 16; }
         const int cin = aux.cin[layer];
+        const int cout = layer < kTowerConvs ? kC : 8;            // the conv1x1 fills accumulator rows 0..7 only
         const float S = wscale[layer];
         __half h[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int ci = ci0 + (u & 1) * 8 + e;
             float w = 0.f;
-            if (ci < cin) w = blob[aux.koff[layer] + ((int64_t)tap * cin + ci) * kC + co] * S;
+            if (ci < cin && co < cout) w = blob[aux.koff[layer] + ((int64_t)tap * cin + ci) * cout + co] * S;
             const __half hi = __float2half_rn(w);
             h[e] = (u & 2) ? __float2half_rn(w - __half2float(hi)) : hi;
         }
@@ -390,16 +435,17 @@ __global__ void wpack_kernel(const float *__restrict__ blob, PackAux aux, const 
 int net_ts_prepare(ck_net *net) {
     const NetLayout L = net_layout();
     if (!net->d_wts) {
-        // [packed weights][wscale 8 f][inv 8 f][plane5 81 f]
+        // kCopies x [packed weights], then [wscale 16 f][inv 16 f][plane5 81 f]
         CK_CUDA(cudaMalloc(&net->d_wts, ts::kCopies * ts::kWtsBytes + 1024));
     }
     float *aux = (float *)((uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes);
     ts::PackAux h;
     for (int i = 0; i < 8; ++i) { h.koff[i] = L.conv[i].kernel; h.cin[i] = L.conv[i].cin; }
+    h.koff[8] = L.pol1x1.kernel; h.cin[8] = kC;
     float p5[81];
     for (int i = 0; i <= 80; ++i) p5[i] = (float)((double)i / 80.0);
-    CK_CUDA(cudaMemcpy(aux + 16, p5, sizeof(p5), cudaMemcpyHostToDevice));
-    ts::wscale_kernel<<<8, 256>>>(net->d_blob, h, aux, aux + 8);
+    CK_CUDA(cudaMemcpy(aux + 32, p5, sizeof(p5), cudaMemcpyHostToDevice));
+    ts::wscale_kernel<<<ts::kLayers, 256>>>(net->d_blob, h, aux, aux + 16);
     ts::wpack_kernel<<<1024, 256>>>(net->d_blob, h, aux, (uint4 *)net->d_wts);
     CK_CUDA(cudaGetLastError());
     for (int c = 1; c < ts::kCopies; ++c)
@@ -422,7 +468,7 @@ static int launch_tower_ts(ck_net *net, const ts::TowerParams &prm, int64_t max_
     return CK_OK;
 }
 
-int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev, float *d_trunk, float *d_pconv,
+int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev, float *d_pflat, float *d_vconv,
                  cudaStream_t stream, int *launches) {
     if (!net->d_wts) return fail(CK_ERR_NO_NET, "tcgen05 tower: weights were never packed");
     const NetLayout L = net_layout();
@@ -430,10 +476,12 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     ts::TowerParams prm;
     prm.leaves = d_leaves; prm.n_dev = n_dev; prm.max_n = (int32_t)max_n;
     prm.wts = (const uint4 *)net->d_wts; prm.blob = net->d_blob; prm.fold = net->d_scale;
-    prm.inv_scale = aux + 8;
-    prm.plane5 = aux + 16;
+    prm.inv_scale = aux + 16;
+    prm.plane5 = aux + 32;
     for (int i = 0; i < 8; ++i) prm.bias_off[i] = L.conv[i].bias;
-    prm.trunk = d_trunk; prm.pconv = d_pconv;
+    prm.bias_off[8] = L.pol1x1.bias;
+    prm.val1x1_k = L.val1x1.kernel; prm.val1x1_b = L.val1x1.bias;
+    prm.pflat = d_pflat; prm.vconv = d_vconv;
     static const int variant = [] { const char *v = getenv("CK_TS_VARIANT"); return v ? atoi(v) : 0; }();
     (void)variant;
     const int rc = launch_tower_ts<8>(net, prm, max_n, stream);
