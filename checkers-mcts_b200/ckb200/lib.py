@@ -72,6 +72,8 @@ def _load():
     L.ck_net_set_weights_device.argtypes = [vp, vp, i64]
     L.ck_net_forward.argtypes = [vp, vp, i64, vp, vp]
     L.ck_net_forward_planes.argtypes = [vp, vp, i64, vp, vp]
+    L.ck_movegen_csr.argtypes = [C.c_int, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.ck_movegen_csr_device.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, vp]
     L.ck_net_forward_device.argtypes = [vp, vp, i64, vp, vp, vp]
     L.ck_mask_renorm.argtypes = [C.c_int, vp, vp, i64, vp]
     L.ck_engine_create.argtypes = [C.POINTER(EngineCfg)]
@@ -142,6 +144,23 @@ def movegen(pos, device=0, max_children=MAX_CHILDREN, want_children=True):
     check(_lib.ck_movegen(device, _ptr(pos), n, max_children, _ptr(children), _ptr(counts), _ptr(masks),
                           _ptr(status), _ptr(plane5)))
     return dict(children=children, counts=counts, masks=masks, status=status, plane5=plane5)
+
+
+def movegen_csr(pos, device=0):
+    """Packed successors: dict(children [total] POS_DTYPE, offsets [n+1] uint32, masks, status, plane5); the
+    successors of position i are children[offsets[i]:offsets[i+1]] in the reference's list order."""
+    pos = np.ascontiguousarray(pos, dtype=POS_DTYPE)
+    n = len(pos)
+    offsets = np.zeros(n + 1, dtype=np.uint32)
+    check(_lib.ck_movegen_csr(device, _ptr(pos), n, None, 0, _ptr(offsets), None, None, None))   # sizes only
+    total = int(offsets[n])
+    children = np.zeros(max(total, 1), dtype=POS_DTYPE)
+    masks = np.zeros((n, 8), dtype=np.uint32)
+    status = np.zeros(n, dtype=np.uint8)
+    plane5 = np.zeros(n, dtype=np.uint8)
+    check(_lib.ck_movegen_csr(device, _ptr(pos), n, _ptr(children), total, _ptr(offsets), _ptr(masks), _ptr(status),
+                              _ptr(plane5)))
+    return dict(children=children[:total], offsets=offsets, masks=masks, status=status, plane5=plane5)
 
 
 def rollout(pos, seed, device=0, max_plies=0):

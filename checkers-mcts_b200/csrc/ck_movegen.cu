@@ -46,6 +46,101 @@ movegen_kernel(const uint4 *__restrict__ pos, int64_t n, int max_children, ck_po
     }
 }
 
+// ---- K1, packed output -------------------------------------------------------------------
+// Same successors as movegen_kernel, written back to back (CSR): the children of position i are
+// children[offsets[i] .. offsets[i+1]) in the reference's list order.  The strided [n][max_children]
+// layout touches 768 B of address space per position to store ~70 B, which is what kept K1 at 15 % of
+// the HBM roofline; here the kernel moves the algorithmic bytes only (16 B in, 4 B offset, 32 B mask,
+// 2 B status/plane5 and 16 B per child out).  One pass: tiles of 256 positions take a ticket, scan
+// their counts (warp shuffles + shared memory) and chain the tile totals with a decoupled look-back
+// over 64-bit {flag, value} words, so offsets are deterministic and no second sweep is needed.
+constexpr int kCsrTile = 256;
+constexpr unsigned long long kCsrAgg = 1ull << 62, kCsrIncl = 2ull << 62, kCsrVal = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(kCsrTile)
+movegen_csr_kernel(const uint4 *__restrict__ pos, int64_t n, ck_pos *__restrict__ children, uint32_t child_cap,
+                   uint32_t *__restrict__ offsets, uint4 *__restrict__ masks, uint8_t *__restrict__ status,
+                   uint8_t *__restrict__ plane5, unsigned int *__restrict__ ticket, unsigned long long *__restrict__ tile_state) {
+    __shared__ unsigned int s_tile;
+    __shared__ uint32_t s_warp_tot[kCsrTile / 32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);          // tiles are chained in ticket order: every predecessor is already running
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t i = (int64_t)tile * kCsrTile + tid;
+    ck_pos p;
+    p.p1 = p.p2 = p.k = p.meta = 0;
+    uint32_t mask[8];
+    int cnt = 0;
+    if (i < n) {
+        const uint4 v = __ldg(pos + i);
+        p.p1 = v.x; p.p2 = v.y; p.k = v.z; p.meta = v.w;
+        cnt = gen_moves(p, NullSink{}, mask);
+        int p5;
+        const int st = outcome_of(p, cnt > 0, &p5);
+        if (masks) {
+            masks[2 * i] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
+            masks[2 * i + 1] = make_uint4(mask[4], mask[5], mask[6], mask[7]);
+        }
+        if (status) status[i] = (uint8_t)st;
+        if (plane5) plane5[i] = (uint8_t)p5;
+    }
+    // exclusive scan of the counts inside the tile
+    uint32_t incl = (uint32_t)cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[w] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, tile_total = 0;
+#pragma unroll
+    for (int q = 0; q < kCsrTile / 32; ++q) {
+        const uint32_t v = s_warp_tot[q];
+        if (q < w) warp_off += v;
+        tile_total += v;
+    }
+    const uint32_t loc = warp_off + incl - (uint32_t)cnt;
+    // chain the tile totals (decoupled look-back, one warp, 32 predecessors per probe)
+    if (w == 0) {
+        unsigned long long base = 0;
+        if (lane == 0) atomicExch(tile_state + tile, (tile == 0 ? kCsrIncl : kCsrAgg) | tile_total);
+        if (tile > 0) {
+            int64_t look = (int64_t)tile - 1;
+            for (;;) {
+                const int64_t idx = look - lane;
+                unsigned long long v = kCsrIncl;                       // before tile 0: inclusive prefix 0
+                if (idx >= 0) v = *reinterpret_cast<volatile unsigned long long *>(tile_state + idx);
+                if (__any_sync(0xFFFFFFFFu, (v >> 62) == 0)) continue; // a predecessor has not published yet
+                const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+                const int first = incl_mask ? __ffs((int)incl_mask) - 1 : 31;
+                unsigned long long part = lane <= first ? (v & kCsrVal) : 0ull;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+                base += part;
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(tile_state + tile, kCsrIncl | (base + tile_total));
+        }
+        if (lane == 0) {
+            s_base = base;
+            if ((int64_t)(tile + 1) * kCsrTile >= n && offsets) offsets[n] = (uint32_t)(base + tile_total);
+        }
+    }
+    __syncthreads();
+    const unsigned long long off = s_base + loc;
+    if (i < n) {
+        if (offsets) offsets[i] = (uint32_t)off;
+        if (children != nullptr && cnt > 0) {
+            const int room = off >= child_cap ? 0 : (int)min((unsigned long long)cnt, (unsigned long long)child_cap - off);
+            if (room > 0) gen_moves(p, ArraySink{children + off, room}, mask);
+        }
+    }
+}
+
 // ---- K4 ------------------------------------------------------------------------------
 // MCTS.default_policy without a net (MCTS.py:132-143): uniform random legal successors until
 // determine_outcome reports the end of the game.  Integer-ALU bound; 16 B in, 5 B out.
@@ -127,6 +222,36 @@ int ck_movegen_device(const ck_pos *d_pos, int64_t n, int32_t max_children, ck_p
     return CK_OK;
 }
 
+static void *g_csr_ws[64] = {nullptr};
+static size_t g_csr_ws_bytes[64] = {0};
+
+int ck_movegen_csr_device(const ck_pos *d_pos, int64_t n, ck_pos *d_children, int64_t child_cap, uint32_t *d_offsets,
+                          uint32_t *d_masks, uint8_t *d_status, uint8_t *d_plane5, void *stream) {
+    if (n < 0 || n > (1ll << 26) || child_cap < 0 || child_cap > 0xFFFFFFFFll || !d_pos)
+        return fail(CK_ERR_ARG, "ck_movegen_csr_device: bad n / child_cap (n <= 2^26, child_cap < 2^32)");
+    int dev = 0;
+    CK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(CK_ERR_ARG, "ck_movegen_csr_device: device index out of range");
+    if (n == 0) {
+        if (d_offsets) CK_CUDA(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t), (cudaStream_t)stream));
+        return CK_OK;
+    }
+    const int64_t tiles = (n + kCsrTile - 1) / kCsrTile;
+    const size_t need = 16 + (size_t)tiles * sizeof(unsigned long long);      // [ticket, pad][tile states]
+    if (g_csr_ws_bytes[dev] < need) {
+        CK_CUDA(cudaDeviceSynchronize());
+        cudaFree(g_csr_ws[dev]); g_csr_ws[dev] = nullptr; g_csr_ws_bytes[dev] = 0;
+        CK_CUDA(cudaMalloc(&g_csr_ws[dev], need));
+        g_csr_ws_bytes[dev] = need;
+    }
+    CK_CUDA(cudaMemsetAsync(g_csr_ws[dev], 0, need, (cudaStream_t)stream));
+    movegen_csr_kernel<<<(unsigned)tiles, kCsrTile, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)d_pos, n, d_children, (uint32_t)child_cap, d_offsets, (uint4 *)d_masks, d_status, d_plane5,
+        (unsigned int *)g_csr_ws[dev], (unsigned long long *)((uint8_t *)g_csr_ws[dev] + 16));
+    CK_CUDA(cudaGetLastError());
+    return CK_OK;
+}
+
 int ck_movegen(int device, const ck_pos *pos, int64_t n, int32_t max_children, ck_pos *children,
                int32_t *counts, uint32_t *masks, uint8_t *status, uint8_t *plane5) {
     if (n < 0 || !pos) return fail(CK_ERR_ARG, "ck_movegen: bad arguments");
@@ -153,6 +278,38 @@ int ck_movegen(int device, const ck_pos *pos, int64_t n, int32_t max_children, c
     CK_TRY(cudaDeviceSynchronize());
     if (children) CK_TRY(cudaMemcpy(children, d_ch, n * max_children * sizeof(ck_pos), cudaMemcpyDeviceToHost));
     if (counts) CK_TRY(cudaMemcpy(counts, d_cnt, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (masks) CK_TRY(cudaMemcpy(masks, d_mask, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (status) CK_TRY(cudaMemcpy(status, d_st, n, cudaMemcpyDeviceToHost));
+    if (plane5) CK_TRY(cudaMemcpy(plane5, d_p5, n, cudaMemcpyDeviceToHost));
+    cleanup();
+    return CK_OK;
+}
+
+int ck_movegen_csr(int device, const ck_pos *pos, int64_t n, ck_pos *children, int64_t child_cap, uint32_t *offsets,
+                   uint32_t *masks, uint8_t *status, uint8_t *plane5) {
+    if (n < 0 || !pos || !offsets || child_cap < 0) return fail(CK_ERR_ARG, "ck_movegen_csr: bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(CK_ERR_CUDA, "ck_movegen_csr: cannot select CUDA device " + std::to_string(device));
+    if (n == 0) { offsets[0] = 0; return CK_OK; }
+    ck_pos *d_pos = nullptr, *d_ch = nullptr;
+    uint32_t *d_off = nullptr, *d_mask = nullptr; uint8_t *d_st = nullptr, *d_p5 = nullptr;
+    int rc = CK_OK;
+    auto cleanup = [&]() { cudaFree(d_pos); cudaFree(d_ch); cudaFree(d_off); cudaFree(d_mask); cudaFree(d_st); cudaFree(d_p5); };
+    CK_TRY(cudaMalloc(&d_pos, n * sizeof(ck_pos)));
+    CK_TRY(cudaMemcpy(d_pos, pos, n * sizeof(ck_pos), cudaMemcpyHostToDevice));
+    CK_TRY(cudaMalloc(&d_off, (n + 1) * sizeof(uint32_t)));
+    if (children && child_cap > 0) CK_TRY(cudaMalloc(&d_ch, child_cap * sizeof(ck_pos)));
+    if (masks) CK_TRY(cudaMalloc(&d_mask, n * 8 * sizeof(uint32_t)));
+    if (status) CK_TRY(cudaMalloc(&d_st, n));
+    if (plane5) CK_TRY(cudaMalloc(&d_p5, n));
+    rc = ck_movegen_csr_device(d_pos, n, d_ch, d_ch ? child_cap : 0, d_off, d_mask, d_st, d_p5, nullptr);
+    if (rc != CK_OK) { cleanup(); return rc; }
+    CK_TRY(cudaDeviceSynchronize());
+    CK_TRY(cudaMemcpy(offsets, d_off, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (d_ch) {
+        const int64_t have = std::min<int64_t>(child_cap, (int64_t)offsets[n]);
+        if (have > 0) CK_TRY(cudaMemcpy(children, d_ch, have * sizeof(ck_pos), cudaMemcpyDeviceToHost));
+    }
     if (masks) CK_TRY(cudaMemcpy(masks, d_mask, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (status) CK_TRY(cudaMemcpy(status, d_st, n, cudaMemcpyDeviceToHost));
     if (plane5) CK_TRY(cudaMemcpy(plane5, d_p5, n, cudaMemcpyDeviceToHost));

@@ -59,6 +59,18 @@ int ck_movegen_device(const ck_pos *d_pos, int64_t n, int32_t max_children, ck_p
                       int32_t *d_counts, uint32_t *d_masks, uint8_t *d_status, uint8_t *d_plane5,
                       void *stream);
 
+/* Packed (CSR) variant on device buffers: the successors of position i are
+ * d_children[d_offsets[i] .. d_offsets[i+1]) in the same list order, d_offsets has n+1 entries
+ * (d_offsets[n] = total).  Successors that would land at or beyond child_cap are not written
+ * (d_offsets still reports the full sizes, so a caller can size the buffer with d_children = NULL
+ * first).  n <= 2^26.  This is the layout the cfg4 sweep is measured on: it moves only the
+ * algorithmic bytes of SURVEY.md 8(d).  Calls on one device must not overlap (shared workspace). */
+int ck_movegen_csr(int device, const ck_pos *pos, int64_t n, ck_pos *children, int64_t child_cap,
+                   uint32_t *offsets, uint32_t *masks, uint8_t *status, uint8_t *plane5);   /* host buffers */
+int ck_movegen_csr_device(const ck_pos *d_pos, int64_t n, ck_pos *d_children, int64_t child_cap,
+                          uint32_t *d_offsets, uint32_t *d_masks, uint8_t *d_status, uint8_t *d_plane5,
+                          void *stream);
+
 /* ---- K4: random playouts -----------------------------------------------------------
  * MCTS.default_policy, non-NN branch (MCTS.py:132-143): uniformly random legal moves to
  * the end of the game.  outcome[i] CK_*; plies[i] the playout length.  max_plies <= 0:

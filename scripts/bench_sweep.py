@@ -77,14 +77,38 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
-        ms = float(np.median(times))
+        ms_strided = float(np.median(times))
         b = float(d_counts.float().mean().item())
         bytes_alg = n * (16 + 4 + 32 + 1 + 1 + 16 * b)
+        # packed (CSR) output: the layout the roofline is quoted on
+        total = int(d_counts.sum().item())
+        d_packed = torch.zeros((max(total, 1), 4), dtype=torch.int32, device="cuda")
+        d_off = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+
+        def launch_csr():
+            L.check(lib.ck_movegen_csr_device(C.c_void_p(d_pos.data_ptr()), n, C.c_void_p(d_packed.data_ptr()), total,
+                                              C.c_void_p(d_off.data_ptr()), C.c_void_p(d_masks.data_ptr()),
+                                              C.c_void_p(d_status.data_ptr()), C.c_void_p(d_p5.data_ptr()), C.c_void_p(stream)))
+        for _ in range(3):
+            launch_csr()
+        torch.cuda.synchronize()
+        assert int(d_off[-1].item()) == total
+        times = []
+        for _ in range(args.iters):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            launch_csr()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times))
         # random playouts (K4)
         t0 = time.time()
         outcome, plies = L.rollout(pos, seed=1)
         roll_s = time.time() - t0
-        line = {"workload": "cfg4 movegen/rollout sweep", "positions": n, "movegen_ms": ms,
+        line = {"workload": "cfg4 movegen/rollout sweep", "positions": n, "movegen_ms": ms, "movegen_strided_ms": ms_strided,
+                "layout": "packed CSR (ck_movegen_csr_device; timing includes the workspace memset); strided = [n][48] ck_movegen_device",
                 "positions_per_sec": n / (ms / 1e3), "mean_children": b,
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
                              "frac": bytes_alg / (ms / 1e3) / 1e9 / hbm, "alg_bytes_per_position": bytes_alg / n},

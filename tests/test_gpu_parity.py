@@ -110,6 +110,45 @@ def test_movegen_large_batch_properties(lib):
     assert (big["status"] == ref["status"][idx]).all()
 
 
+def test_movegen_csr_matches_strided_and_oracle(lib):
+    """packed (CSR) K1: same successors, in the same order, as the strided kernel and the oracle, for
+    ragged batches (empty, one position, tile boundaries of 256, many tiles for the look-back chain)."""
+    rng = np.random.RandomState(11)
+    walk = []
+    pos = O.start_position()
+    for _ in range(700):
+        walk.append(pos)
+        kids, _, st, _ = O.movegen(pos)
+        pos = O.start_position() if st != codec.ONGOING else kids[rng.randint(len(kids))]
+    arr = _pos_arr(lib, walk)
+    out0 = lib.movegen_csr(arr[:0])
+    assert list(out0["offsets"]) == [0] and len(out0["children"]) == 0
+    for n in (1, 255, 256, 257, 700):
+        sub = arr[:n]
+        ref = lib.movegen(sub)
+        out = lib.movegen_csr(sub)
+        off = out["offsets"].astype(np.int64)
+        assert (np.diff(off) == ref["counts"]).all() and off[0] == 0 and off[-1] == len(out["children"])
+        assert (out["masks"] == ref["masks"]).all() and (out["status"] == ref["status"]).all()
+        assert (out["plane5"] == ref["plane5"]).all()
+        for i in range(n):
+            a = out["children"][off[i]:off[i + 1]]
+            assert a.tobytes() == ref["children"][i, :ref["counts"][i]].tobytes()
+    for i in rng.randint(0, 700, size=40):                       # and directly against the oracle
+        kids, mask, st, p5 = O.movegen(walk[i])
+        a = out["children"][off[i]:off[i + 1]]
+        assert [tuple(int(v) for v in c) for c in a] == kids
+    # 2^20 positions: 4096 tiles chained by the look-back; offsets must be the exact prefix sums
+    idx = rng.randint(0, 700, size=1 << 20)
+    big = lib.movegen_csr(arr[idx])
+    cnt = ref["counts"][idx].astype(np.int64)
+    exp = np.concatenate([[0], np.cumsum(cnt)])
+    assert (big["offsets"].astype(np.int64) == exp).all()
+    for i in rng.randint(0, 1 << 20, size=200):
+        a = big["children"][exp[i]:exp[i + 1]]
+        assert a.tobytes() == ref["children"][idx[i], :cnt[i]].tobytes()
+
+
 # ---- Checkers.predict glue -----------------------------------------------------------------
 def test_mask_renorm_golden(lib):
     g = np.load(os.path.join(GOLDEN, "predict_glue.npz"))
