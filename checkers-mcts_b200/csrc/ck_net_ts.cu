@@ -51,10 +51,10 @@ constexpr int kLoaderWarps = 8;                     // two sets of four (one war
 constexpr int kLoadGroup = 4;                       // k-steps a loader warp fetches per batch
 constexpr float kActScale = 16.0f;                  // activations are stored as a * 2^4
 constexpr size_t kWtsBytes = (size_t)kG * 8192;     // [k-step][unit 4][co 128][16 B]
-// Every CTA streams the same 4.2 MB in near lock-step, which concentrates the reads of all 148 SMs on
-// the few L2 slices that hold the current window (profiles/r1e: loaders stalled on the loads while
-// lts throughput sat at 7 %).  The packed weights are therefore replicated; CTA b reads copy b % kCopies.
-constexpr int kCopies = 8;
+// All CTAs stream the same 4.3 MB (L2-resident after the first tile pair).  kCopies > 1 replicates the
+// packed weights so that CTA b reads copy b % kCopies; measured no difference on B200 (the L2 serves the
+// lock-step readers from one copy at the same rate), so one copy is kept.
+constexpr int kCopies = 1;
 constexpr uint32_t kIdesc = make_idesc_f16(128, kN);
 constexpr int kBarOff = 2 * kTileBytes;
 constexpr int kVredOff = kBarOff + 512;               // value conv1x1 partial sums [tile 2][quadrant 4][128 columns] fp32

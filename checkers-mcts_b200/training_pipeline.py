@@ -51,6 +51,54 @@ def load_training_data(filename):
         return pickle.load(file)
 
 
+def save_merged_files(memory, iteration, timestamp):
+    """Save merged training data as one pickle (reference :269-275)."""
+    filename = 'data/training_data/Checkers_Data' + str(iteration) + '_' + timestamp + '.pkl'
+    with open(filename, 'wb') as file:
+        pickle.dump(memory, file)
+    return filename
+
+
+def merge_data(data_fns, iteration):
+    """Merge the per-worker self-play files of one iteration into a single file (reference :277-284);
+    like the reference it returns the merged list, the file name only goes to disk."""
+    training_data = []
+    for fn in data_fns:
+        training_data.extend(load_training_data('data/training_data/' + fn))
+    save_merged_files(training_data, iteration, create_timestamp())
+    return training_data
+
+
+class Keras_Generator(object):
+    """Batch view of a list of self-play records ``[state[15,8,8], probs[8,8,8], q, z]`` with the layout
+    the reference feeds to ``fit`` (:288-307): features = planes 0..13 channels-last ``[B,8,8,14]``,
+    labels = ``[visit probabilities flattened to 512, (q + z) / 2]``.  Indexable and iterable; it does
+    not subclass ``keras.utils.Sequence`` (TensorFlow is not a dependency) but has the same ``len`` /
+    ``__getitem__`` contract, so it can be handed to a Keras or PyTorch training loop unchanged."""
+
+    def __init__(self, data, batch_size):
+        self.data = data
+        self.batch_size = batch_size
+
+    def __len__(self):
+        return int(np.ceil(len(self.data) / float(self.batch_size)))
+
+    def __getitem__(self, idx):
+        if idx < 0 or idx >= len(self):
+            raise IndexError(idx)
+        data = self.data[idx * self.batch_size: (idx + 1) * self.batch_size]
+        states = np.array([e[0][:14] for e in data])
+        states = np.moveaxis(states, 1, -1)
+        probs = np.array([np.array(e[1]).flatten() for e in data])
+        qvals = np.array([e[2] for e in data])
+        zvals = np.array([e[3] for e in data])
+        return (states, [probs, (qvals + zvals) / 2])
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
 def record_params(phase, **kwargs):
     """Document the parameters used in the training pipeline (reference :225-244)."""
     folders = {'selfplay': 'data/training_data/Checkers_SelfPlay_Params_', 'training': 'data/model/Checkers_Training_Params_',

@@ -72,3 +72,54 @@ def test_codec_roundtrip_random_positions():
             pos = O.start_position()
         else:
             pos = kids[rng.randint(len(kids))]
+
+
+def _oracle_reference_records():
+    g = O.Game(O.make_cfg(budget=24, training=True, terminate_cnt=40), "hash")
+    g.play()
+    from ckb200 import lib_types as T
+    return R.to_reference_list(T.records_from_dicts(g.records()))
+
+
+def test_keras_generator_and_merge_data(tmp_path, monkeypatch):
+    """loader side of the self-play wire format: the batcher reproduces
+    Keras_Generator.__getitem__ (reference training_pipeline.py:297-307), merge_data concatenates the
+    per-worker pickles (:277-284)."""
+    import pickle
+    import training_pipeline as TP
+    data = _oracle_reference_records()
+    gen = TP.Keras_Generator(data, 7)
+    assert len(gen) == -(-len(data) // 7)
+    seen = 0
+    for b, (x, (probs, v)) in enumerate(gen):
+        chunk = data[b * 7:(b + 1) * 7]
+        assert x.shape == (len(chunk), 8, 8, 14) and x.dtype == np.float64
+        assert probs.shape == (len(chunk), 512) and v.shape == (len(chunk),)
+        for j, e in enumerate(chunk):
+            assert (x[j] == np.moveaxis(e[0][:14], 0, -1)).all()
+            assert (probs[j] == e[1].reshape(512)).all()
+            assert v[j] == (np.float64(e[2]) + e[3]) / 2          # q is float32 (or a Python int), the batch float64
+        seen += len(chunk)
+    assert seen == len(data)
+    # against the reference class itself where it is mounted (the build container)
+    ref_dir = "/root/reference"
+    if os.path.isdir(ref_dir):
+        from oracle import ref_harness as RH
+        ref_tp = RH.load_reference(with_pipeline=True).training_pipeline
+        rg = ref_tp.Keras_Generator(data, 7)
+        for b in range(len(gen)):
+            x, (probs, v) = gen[b]
+            rx, (rp, rv) = rg[b]                       # reference __len__ uses np.int (gone in numpy 2); __getitem__ runs
+            assert x.tobytes() == rx.tobytes() and probs.tobytes() == rp.tobytes() and v.tobytes() == rv.tobytes()
+    # merge_data
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/training_data")
+    for k in range(3):
+        with open("data/training_data/part%d.pkl" % k, "wb") as f:
+            pickle.dump(data[k::3], f)
+    merged = TP.merge_data(["part0.pkl", "part1.pkl", "part2.pkl"], 5)
+    assert len(merged) == len(data)
+    files = [f for f in os.listdir("data/training_data") if f.startswith("Checkers_Data5_")]
+    assert len(files) == 1
+    back = TP.load_training_data(os.path.join("data/training_data", files[0]))
+    assert len(back) == len(data) and (back[0][0] == data[0][0]).all()
