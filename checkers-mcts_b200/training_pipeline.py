@@ -38,8 +38,8 @@ def load_blob(filename):
     if isinstance(filename, str) and filename.startswith("stub:"):
         return filename[5:]
     if isinstance(filename, str) and filename.endswith(".h5"):
-        raise NotImplementedError("Keras .h5 import is not implemented yet (SURVEY 8f row 2); "
-                                  "convert the weights to a .npy blob (ckb200.net.layout) first")
+        from ckb200 import h5lite                       # the reference's own model files (model.save(...h5), :186-191)
+        return h5lite.keras_h5_to_blob(filename)
     blob = np.load(filename)
     if blob.size != _N.NET_PARAM_COUNT:
         raise ValueError("weight blob %s has %d values, expected %d" % (filename, blob.size, _N.NET_PARAM_COUNT))

@@ -416,3 +416,18 @@ def test_selfplay_with_network(lib):
                 assert sum(r["visits"]) == r["root_n"] - 1
     eng.close()
     net.close()
+
+
+@pytest.mark.parametrize("tower", ["ts", "ss"])
+def test_tower_kernels_agree_with_fp32_path(tower):
+    """both tcgen05 towers (weights-in-TMEM product kernel, shared-memory cross-check) against the fp32
+    CUDA-core path on ragged batch sizes: single tile pair, odd tails, the persistent multi-pair loop.
+    The tower is chosen once per process (CK_TOWER), hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CK_TOWER=tower)
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_tower.py"), "1", "2", "3", "5", "97", "593", "1187", "4099"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count(" ok ") == 8 and "MISMATCH" not in r.stdout

@@ -123,3 +123,42 @@ def test_keras_generator_and_merge_data(tmp_path, monkeypatch):
     assert len(files) == 1
     back = TP.load_training_data(os.path.join("data/training_data", files[0]))
     assert len(back) == len(data) and (back[0][0] == data[0][0]).all()
+
+
+def test_keras_h5_import_of_reference_models():
+    """the reference's shipped .h5 networks are read without h5py/TensorFlow and mapped onto
+    the weight blob by layer topology.  Runs where the reference tree is mounted (the build container)."""
+    import pytest
+    d = "/root/reference/data/model"
+    if not os.path.isdir(d):
+        pytest.skip("reference models not mounted")
+    from ckb200 import h5lite
+    from oracle import net_oracle as NO
+    fns = sorted(f for f in os.listdir(d) if f.endswith(".h5"))
+    assert len(fns) == 11
+    init = [f for f in fns if "Model0_" in f][0]
+    dsets, raw = h5lite.read_datasets(os.path.join(d, init))
+    assert len(dsets) == 70 and sum(a.size for a in dsets.values()) == N.NET_PARAM_COUNT
+    roles = h5lite.layer_roles(h5lite.model_config(raw))
+    assert roles["policy_head"] == "policy_head" and roles["value_head"] == "value_head" and roles["conv0"] == "conv2d"
+    p0 = N.unpack(h5lite.keras_h5_to_blob(os.path.join(d, init)))
+    # iteration 0 is the freshly initialised network: Glorot-uniform kernels, unit BN statistics (SURVEY 8d cfg1)
+    for name, fan in (("conv0/kernel", 9 * 14 + 9 * 128), ("conv3/kernel", 18 * 128), ("policy_head/kernel", 1024)):
+        lim = np.sqrt(6.0 / fan)
+        assert 0.95 * lim < np.abs(p0[name]).max() <= lim * (1 + 1e-6)
+    assert (p0["conv5/bn_var"] == 1).all() and (p0["conv5/bn_gamma"] == 1).all() and (p0["value_dense1/bn_mean"] == 0).all()
+    # a trained iteration: the imported network must put its policy mass on the legal moves of the start
+    # position (it does only if conv / BN / Flatten(x,y,c) / Dense semantics and the layer mapping are right)
+    sp = O.start_position()
+    kids, mask, st, p5 = O.movegen(sp)
+    x = codec.nn_input_planes(sp, mask, p5).reshape(1, 8, 8, 14)
+    legal = np.zeros(512, dtype=bool)
+    for k in kids:
+        legal[codec.meta_action(k[3])] = True
+    last = [f for f in fns if "Model10_" in f][0]
+    import training_pipeline as TP
+    blob = TP.load_blob(os.path.join(d, last))
+    p, v = NO.forward(N.unpack(blob), x)
+    assert p[0][legal].sum() > 0.98 and legal[p[0].argmax()] and abs(v[0]) < 0.5
+    pi, _ = NO.forward(p0, x)
+    assert pi[0][legal].sum() < 0.1                                  # the untrained one does not
