@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "ckb200", "libckb200.so")
-SOURCES = ["ck_movegen.cu", "ck_net.cu", "ck_net_tc.cu", "ck_net_ts.cu", "ck_engine.cu"]
+SOURCES = ["ck_movegen.cu", "ck_net.cu", "ck_net_tc.cu", "ck_net_ts.cu", "ck_heads_tc.cu", "ck_engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

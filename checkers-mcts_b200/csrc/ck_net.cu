@@ -340,6 +340,8 @@ static int net_finish_weights(ck_net *net) {
     if (rc != CK_OK) return rc;
     rc = net_ts_prepare(net);
     if (rc != CK_OK) return rc;
+    rc = net_heads_tc_prepare(net);
+    if (rc != CK_OK) return rc;
     CK_CUDA(cudaDeviceSynchronize());
     net->have_weights = true;
     return CK_OK;
@@ -396,11 +398,19 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
         heads_attr_done = true;
     }
     const unsigned hgrid = (unsigned)((max_n + kHeadPB - 1) / kHeadPB);
-    if (fused)
+    // CK_HEADS=simt keeps the fp32 CUDA-core Dense for the fused path too (cross-check)
+    static const bool heads_simt = [] { const char *v = getenv("CK_HEADS"); return v && v[0] == 's'; }();
+    if (fused && !heads_simt) {
+        // d_act1 = [pflat n x 512 | logits n x 512 | ...], d_act0 = vconv
+        rc = net_heads_tc(net, pconv, trunk, pconv + max_n * 512, max_n, n_dev, d_policy, d_value, stream, &nl);
+        if (rc != CK_OK) return rc;
+    } else if (fused) {
         heads_kernel<true><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
-    else
+        ++nl;
+    } else {
         heads_kernel<false><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
-    ++nl;
+        ++nl;
+    }
     CK_CUDA(cudaGetLastError());
     if (launches) *launches += nl;
     return CK_OK;
@@ -424,7 +434,7 @@ ck_net *ck_net_create(int device) {
 void ck_net_destroy(ck_net *net) {
     if (!net) return;
     DeviceGuard g(net->device);
-    cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack); cudaFree(net->d_wts);
+    cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack); cudaFree(net->d_wts); cudaFree(net->d_hpack);
     cudaFree(net->d_act0); cudaFree(net->d_act1);
     cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value);
     delete net;

@@ -32,6 +32,7 @@ struct ck_net {
     // tcgen05 tower operands (built by ck_net_tc.cu)
     void *d_wpack = nullptr;         // split-fp16 weights in UMMA core-matrix order
     size_t wpack_bytes = 0;
+    void *d_hpack = nullptr;         // policy Dense(512) weights, split fp16, UMMA layout (ck_heads_tc.cu)
     void *d_wts = nullptr;           // split-fp16 weights in k-step order for the weights-in-TMEM tower (ck_net_ts.cu)
     // activation scratch, grown on demand
     int64_t cap = 0;
@@ -63,4 +64,8 @@ int net_tc_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
 int net_ts_prepare(ck_net *net);
 int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
                  float *d_trunk, float *d_pconv, cudaStream_t stream, int *launches);
+// tensor-core policy Dense + fp32 tails of both heads on the fused tower outputs (ck_heads_tc.cu)
+int net_heads_tc_prepare(ck_net *net);
+int net_heads_tc(ck_net *net, const float *d_pflat, const float *d_vconv, float *d_logits, int64_t max_n, const int32_t *n_dev,
+                 float *d_policy, float *d_value, cudaStream_t stream, int *launches);
 }  // namespace ck
