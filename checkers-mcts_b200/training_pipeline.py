@@ -51,6 +51,51 @@ def load_training_data(filename):
         return pickle.load(file)
 
 
+def create_nn(**kwargs):
+    """Randomly initialised policy/value network with the reference's architecture and Keras default
+    initialisers (reference :44-120).  Returns a ``ckb200.train.CheckersNet`` (PyTorch); regularisation and
+    loss weights are taken from the kwargs again by ``train_nn``."""
+    from ckb200 import train as T
+    if kwargs.get('NUM_KERNELS', 128) != 128:
+        raise ValueError('the device evaluator is built for NUM_KERNELS = 128')
+    return T.CheckersNet(seed=kwargs.get('SEED', 0))
+
+
+def train_nn(training_data, neural_network, **kwargs):
+    """Train with the reference's recipe (reference :123-179): Adam + triangular CLR per batch, early stopping
+    and best-epoch checkpoint on val_loss.  ``neural_network`` is a CheckersNet, a weight blob or a weight file
+    (.npy / the reference's .h5).  Returns (history, filename of the best epoch's weights)."""
+    from ckb200 import train as T
+    if isinstance(neural_network, str):
+        neural_network = load_blob(neural_network)
+    return T.train_nn(training_data, neural_network, Keras_Generator, create_timestamp(), **kwargs)
+
+
+def set_nn_lrate(neural_network, lrate):
+    """Kept for API compatibility (reference :181-184): the learning rate is set per batch by the CLR schedule."""
+    neural_network.base_lr = lrate
+
+
+def save_nn_to_disk(neural_network, iteration, timestamp):
+    """Save the network with timestamp and iteration in the file name (reference :186-191); the weights are
+    written as a .npy blob, which every NN_FN consumer of this package accepts."""
+    filename = 'data/model/Checkers_Model' + str(iteration) + '_' + timestamp + '.npy'
+    return neural_network.save(filename)
+
+
+def plot_history(history, nn, TRAINING_ITERATION):
+    """The reference plots loss per epoch with matplotlib (:199-217); without it the curve is written as text."""
+    filename = 'data/plots/Checkers_Model' + str(TRAINING_ITERATION + 1) + '_TrainingLoss_' + create_timestamp() + '.txt'
+    import os
+    os.makedirs(os.path.dirname(filename), exist_ok=True)
+    with open(filename, 'w') as file:
+        file.write('epoch loss val_loss lr\n')
+        for i, loss in enumerate(history['loss']):
+            val = history['val_loss'][i] if i < len(history.get('val_loss', [])) else float('nan')
+            file.write('%d %.6f %.6f %.3e\n' % (i + 1, loss, val, history['lr'][i]))
+    return filename
+
+
 def save_merged_files(memory, iteration, timestamp):
     """Save merged training data as one pickle (reference :269-275)."""
     filename = 'data/training_data/Checkers_Data' + str(iteration) + '_' + timestamp + '.pkl'

@@ -12,6 +12,7 @@ oracle (``oracle/ck_oracle.c``) against the real reference where it is mounted.
 """
 import contextlib
 import importlib
+import importlib.machinery
 import os
 import sys
 import types
@@ -25,6 +26,8 @@ def reference_available():
 
 def _stub(name, **attrs):
     m = types.ModuleType(name)
+    # a spec keeps importlib.util.find_spec(name) (PyTorch probes for TensorFlow that way) from raising
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
     m.__dict__.update(attrs)
     sys.modules[name] = m
     return m

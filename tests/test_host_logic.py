@@ -162,3 +162,55 @@ def test_keras_h5_import_of_reference_models():
     assert p[0][legal].sum() > 0.98 and legal[p[0].argmax()] and abs(v[0]) < 0.5
     pi, _ = NO.forward(p0, x)
     assert pi[0][legal].sum() < 0.1                                  # the untrained one does not
+
+
+def test_training_step_matches_reference_recipe(tmp_path, monkeypatch):
+    """the PyTorch training network equals the float64 restatement on the same blob, blobs
+    round-trip, the CLR schedule is the reference's triangular formula, and a short train_nn run lowers
+    the loss and writes the best epoch's weights."""
+    import torch
+    import training_pipeline as TP
+    from ckb200 import train as T
+    from oracle import net_oracle as NO
+    blob = N.random_init_blob(3, 0.2)
+    model = T.CheckersNet(blob)
+    assert (model.blob() == blob).all()                                      # Keras layouts <-> torch layouts
+    data = _oracle_reference_records()
+    gen = TP.Keras_Generator(data, 16)
+    x, (probs, v) = gen[0]
+    kp, kv = model.predict(x)
+    rp, rv = NO.forward(N.unpack(blob), np.asarray(x, dtype=np.float32))
+    assert np.abs(kp - rp).max() < 1e-5 and np.abs(kv.reshape(-1) - rv).max() < 1e-5
+    # CLR: triangular, base at 0 and 2*step, max at step (CLR/clr_callback.py:105-111)
+    assert T.clr_triangular(0, 5e-5, 1e-2, 40) == 5e-5 and abs(T.clr_triangular(40, 5e-5, 1e-2, 40) - 1e-2) < 1e-12
+    assert abs(T.clr_triangular(20, 5e-5, 1e-2, 40) - (5e-5 + (1e-2 - 5e-5) * 0.5)) < 1e-12
+    assert abs(T.clr_triangular(80, 5e-5, 1e-2, 40) - 5e-5) < 1e-12 and abs(T.clr_triangular(100, 5e-5, 1e-2, 40) - (5e-5 + (1e-2 - 5e-5) * 0.5)) < 1e-12
+    # loss = CE + MSE + L2 over kernels and biases
+    xt = torch.as_tensor(np.asarray(x, dtype=np.float32))
+    loss, ce, mse = T.loss_terms(model.eval(), xt, torch.as_tensor(np.asarray(probs, dtype=np.float32)), torch.as_tensor(np.asarray(v, dtype=np.float32)))
+    p = N.unpack(blob)
+    l2 = sum(float((p[k].astype(np.float64) ** 2).sum()) for k in p if k.endswith("/kernel") or k.endswith("/bias")) * 1e-3
+    ref_ce = float(-(np.asarray(probs) * np.log(np.clip(rp, 1e-7, None))).sum(1).mean())
+    ref_mse = float(((rv - np.asarray(v)) ** 2).mean())
+    assert abs(ce.item() - ref_ce) < 1e-4 and abs(mse.item() - ref_mse) < 1e-5 and abs(loss.item() - (ref_ce + ref_mse + l2)) < 1e-3
+    # a short run
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/model")
+    np.random.seed(0); torch.manual_seed(0)
+    kw = dict(TRAINING_ITERATION=0, NN_BASE_LR=5e-5, NN_MAX_LR=2e-3, CLR_SS_COEFF=4, BATCH_SIZE=16, EPOCHS=3, CONV_REG=1e-3,
+              DENSE_REG=1e-3, NUM_KERNELS=128, VAL_SPLIT=0.2, MIN_DELTA=0.01, PATIENCE=20, POLICY_LOSS_WEIGHT=1.0, VALUE_LOSS_WEIGHT=1.0)
+    nn0 = TP.create_nn(**kw)
+    hist, fn = TP.train_nn(list(data), nn0, **dict(kw, device="cpu", verbose=False))
+    assert len(hist["loss"]) == 3 and hist["loss"][-1] < hist["loss"][0] and len(hist["val_loss"]) == 3
+    assert fn.startswith("data/model/Checkers_Model1_") and os.path.exists(fn)
+    out = TP.load_blob(fn)
+    assert out.shape == (N.NET_PARAM_COUNT,) and (out != N.random_init_blob(0)).any()
+    assert os.path.exists(TP.plot_history(hist, nn0, 0))
+    # the reference's own CyclicLR where it is mounted (last: its import leaves TensorFlow stubs in sys.modules)
+    if os.path.isdir("/root/reference"):
+        from oracle import ref_harness as RH
+        ref = RH.load_reference(with_pipeline=True).training_pipeline
+        clr = ref.CyclicLR(base_lr=5e-5, max_lr=1e-2, step_size=40, mode='triangular')
+        for it in (0, 7, 40, 63, 80, 131):
+            clr.clr_iterations = float(it)
+            assert abs(float(clr.clr()) - T.clr_triangular(it, 5e-5, 1e-2, 40)) < 1e-15
