@@ -295,3 +295,73 @@ class tournament_Checkers(object):
             file.write(tabulate(game_outcomes, tablefmt='fancy_grid',
                                 headers=['Game Number', 'Player 1', 'Player 2', 'Outcome', 'Turn Count']))
         return filename
+
+
+class final_evaluation(object):
+    """Round-robin among trained models (reference :603-719): every model plays every other model twice (once
+    as each colour); a win scores +1 for the winner and -1 for the loser in the pairing table, the row sums are
+    the models' points.  Results go to data/final_eval/ as a fancy_grid table plus the points per model
+    iteration as text (the reference plots them with matplotlib)."""
+
+    def __init__(self, model_iter_list, tourney_kwargs, mcts_kwargs):
+        self.model_iter_list = list(model_iter_list)
+        self.model_fn_list = []
+        self.tourney_kwargs = dict(tourney_kwargs)
+        self.mcts_kwargs = mcts_kwargs
+        self.num_cpus = tourney_kwargs['NUM_CPUS']
+        self.tourney_kwargs['TOURNEY_GAMES'] = 2
+        fns = sorted(os.listdir('data/model'))
+        for iter_num in self.model_iter_list:
+            for fn in fns:
+                if 'Model' + str(iter_num) + '_' in fn and (fn.endswith('.h5') or fn.endswith('.npy')):
+                    self.model_fn_list.append(fn)
+                    break
+        if len(self.model_fn_list) != len(self.model_iter_list):
+            raise ValueError('Model(s) not found!')
+        self.table = np.zeros((len(self.model_iter_list), len(self.model_iter_list)))
+        self.game_outcomes = []
+
+    def start_evaluation(self, num_cpus=1):
+        """num_cpus is accepted for compatibility; each pairing is one two-game arena on the GPU"""
+        model_fn_list = self.model_fn_list.copy()
+        for _ in range(len(self.model_fn_list) - 1):
+            new_nn_fn = model_fn_list.pop()
+            game_outcomes = []
+            for old_nn_fn in model_fn_list:
+                game_outcomes.extend(self._wrapper_func(new_nn_fn, old_nn_fn))
+            self.game_outcomes.append(game_outcomes)
+        filename = self._parse_tourney_results()
+        print('Final evaluation over!  View results in final_eval folder!')
+        return filename
+
+    def _wrapper_func(self, new_nn_fn, old_nn_fn):
+        tourney_kwargs = dict(self.tourney_kwargs, NUM_CPUS=1, NEW_NN_FN='data/model/' + new_nn_fn,
+                              OLD_NN_FN='data/model/' + old_nn_fn)
+        mcts_kwargs = dict(self.mcts_kwargs, NN_FN=tourney_kwargs['NEW_NN_FN'])
+        print('Beginning tournament between {} and {}!'.format(tourney_kwargs['NEW_NN_FN'], tourney_kwargs['OLD_NN_FN']))
+        return tournament_Checkers(tourney_kwargs, mcts_kwargs)._start_tournament()
+
+    def _parse_tourney_results(self):
+        for game_outcomes in self.game_outcomes:
+            for _game_num, p1_fn, p2_fn, outcome, _move_count in game_outcomes:
+                p1_idx = self.model_fn_list.index(os.path.basename(p1_fn))
+                p2_idx = self.model_fn_list.index(os.path.basename(p2_fn))
+                if outcome == 'player1_wins':
+                    self.table[p1_idx, p2_idx] += 1
+                    self.table[p2_idx, p1_idx] -= 1
+                elif outcome == 'player2_wins':
+                    self.table[p1_idx, p2_idx] -= 1
+                    self.table[p2_idx, p1_idx] += 1
+        model_scores = np.sum(self.table, axis=1)
+        self.model_scores = model_scores
+        stamp = create_timestamp()
+        os.makedirs('data/final_eval', exist_ok=True)
+        with open('data/final_eval/Checkers_Final_Evaluation_' + stamp + '_points.txt', 'w') as file:
+            for it, score in zip(self.model_iter_list, model_scores):
+                file.write('{} {}\n'.format(it, score))
+        table = np.hstack((self.table, np.transpose(model_scores[np.newaxis])))
+        filename = 'data/final_eval/Checkers_Final_Evaluation_' + stamp + '.txt'
+        with open(filename, 'w') as file:
+            file.write(tabulate(table, headers=self.model_iter_list + ['Total'], showindex=self.model_iter_list,
+                                tablefmt='fancy_grid'))
+        return filename

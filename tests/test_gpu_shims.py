@@ -145,3 +145,24 @@ def test_tournament_matches_reference_golden(mods, tmp_path, monkeypatch):
     fn = tour.start_tournament()
     txt = open(fn, encoding="utf-8").read()
     assert fn.startswith("data/tournament_results/Tournament_") and "Wins/Losses/Draws" in txt and "Turn Count" in txt
+
+
+def test_final_evaluation_round_robin(mods, tmp_path, monkeypatch):
+    """final_evaluation (reference training_pipeline.py:603-719): three models, every pairing plays two
+    games; the pairing table is antisymmetric and the points are its row sums."""
+    _, _, T = mods
+    from ckb200 import net as N
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/model")
+    for it in (0, 1, 2):
+        np.save("data/model/Checkers_Model%d_01-Jan-2021(00:00:0%d).npy" % (it, it), N.random_init_blob(it))
+    fe = T.final_evaluation([0, 1, 2], dict(TRAINING_ITERATION=2, OLD_NN_FN=None, NEW_NN_FN=None, TOURNEY_GAMES=2, NUM_CPUS=1, SEED=7),
+                            dict(MCTS_KW, BUDGET=6, NEURAL_NET=True, TRAINING=False, DIRICHLET_EPSILON=0.25, TEMPERATURE_TAU=0))
+    assert [f.split("_")[1] for f in fe.model_fn_list] == ["Model0", "Model1", "Model2"]
+    fn = fe.start_evaluation(num_cpus=4)
+    assert sum(len(g) for g in fe.game_outcomes) == 6                     # 3 pairings x 2 games
+    assert (fe.table == -fe.table.T).all() and (fe.model_scores == fe.table.sum(1)).all()
+    txt = open(fn, encoding="utf-8").read()
+    assert fn.startswith("data/final_eval/Checkers_Final_Evaluation_") and "Total" in txt
+    with pytest.raises(ValueError):
+        T.final_evaluation([0, 5], dict(NUM_CPUS=1), MCTS_KW)
