@@ -340,10 +340,32 @@ __device__ void compact_tree(const WarpCtx &c, int t, int root) {
             if (c.lane >= o) incl += v;
         }
         const int total = __shfl_sync(CK_FULL, incl, 31);
-        const int nfc = count + incl - nch;
-        if (nch > 0) {
-            for (int k = 0; k < nch; ++k) { dpos[nfc + k] = spos[ofc + k]; dstat[nfc + k] = sstat[ofc + k]; }
-            dstat[i].w = (link & ~kFcMask) | (uint32_t)nfc;
+        const int excl = incl - nch;
+        if (nch > 0) dstat[i].w = (link & ~kFcMask) | (uint32_t)(count + excl);
+        // The children of this round's (up to 32) parents go to [count, count + total) in parent order.
+        // One lane per destination node: the parent is found by a shuffle binary search over the
+        // exclusive prefix sums, and four steps of loads are issued before their stores so that the
+        // round costs about two memory round trips instead of one per child of the widest parent
+        // (the serial per-lane copy made a re-rooting slot the tail of every tree_step launch).
+        for (int j0 = 0; j0 < total; j0 += 128) {
+            uint4 vp[4], vs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + c.lane;
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int e = __shfl_sync(CK_FULL, excl, (lo + step) & 31);
+                    if (lo + step < 32 && e <= j) lo += step;                // largest parent with excl <= j
+                }
+                const int src = __shfl_sync(CK_FULL, ofc, lo) + (j - __shfl_sync(CK_FULL, excl, lo));
+                if (j < total) { vp[u] = spos[src]; vs[u] = sstat[src]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + c.lane;
+                if (j < total) { dpos[count + j] = vp[u]; dstat[count + j] = vs[u]; }
+            }
         }
         count += total;
         head = end;
@@ -739,13 +761,27 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     d.n_slots = cfg->n_slots;
     d.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 2048;
     int cap = cfg->pool_cap;
-    if (cap <= 0) { cap = 32768; while (cap < 3 * cfg->budget * 24) cap *= 2; }
+    if (cap <= 0) {
+        // default: as many nodes per tree buffer as 40 % of the free HBM allows (up to 128 Ki), so that a
+        // tree is compacted once or twice per game rather than every few moves; never below what one
+        // search can allocate
+        cap = 32768;
+        while (cap < 3 * cfg->budget * 24) cap *= 2;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            while (cap < 131072 && (size_t)cfg->n_slots * 3 * (size_t)(2 * cap) * 2 * sizeof(uint4) <= free_b / 5 * 2) cap *= 2;
+        }
+    }
     if (cap > (int)kFcMask) cap = (int)kFcMask;
     d.cap = cap;
     int need = cfg->budget * CK_MAX_CHILDREN;            // room for a whole search in the worst case
     if (need > cap / 2) need = cap / 2;
     d.compact_need = need;
-    d.max_term = cfg->max_terminal_sims_per_step > 0 ? cfg->max_terminal_sims_per_step : 64;
+    // Simulations that end in a terminal child need no evaluation and are finished inside the round; a
+    // slot near the end of its game would chain dozens of them and become the tail of the launch (at 64
+    // per round the steady-state tree_step took 0.35 ms instead of 0.1 ms: scripts/long_run.py), so the
+    // default lets a slot finish four and carries the rest into the next rounds.
+    d.max_term = cfg->max_terminal_sims_per_step > 0 ? cfg->max_terminal_sims_per_step : 4;
     d.one_minus_eps = (float)(1.0 - cfg->epsilon);       // (1 - eps) * float32 array stays float32 (numpy >= 2)
     if (cfg->keep_records) d.max_rec = (cfg->terminate_cnt > 0 ? cfg->terminate_cnt : d.max_plies) + 1;
     CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

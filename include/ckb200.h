@@ -136,7 +136,7 @@ typedef struct {
     int32_t reference_tau_quirk; /* 1: tau is never reset between games */
     int32_t game_id_base;     /* global id of local game i = base + i*stride (multi-GPU sharding) */
     int32_t game_id_stride;   /* 0 is treated as 1 */
-    int32_t max_terminal_sims_per_step; /* 0: default 64 */
+    int32_t max_terminal_sims_per_step; /* simulations ending in a terminal child that a slot may finish inside one round; 0: default 4 */
     int32_t compact_always;   /* 1: compact the kept subtree at every re-root (default: only when the pool runs low) */
     int32_t reserved0;
 } ck_engine_cfg;
