@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
         return OUT
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("CK_NVCC_DEFS", "").split()   # tuning experiments: -DNAME=value
     objs = []
     procs = []
     for src in SOURCES:

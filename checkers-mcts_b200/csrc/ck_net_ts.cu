@@ -50,6 +50,10 @@ constexpr int kWCol0 = 256;                         // first weight column; accu
 constexpr int kLoaderWarps = 8;                     // two sets of four (one warp per TMEM lane quadrant)
 constexpr int kLoadGroup = 4;                       // k-steps a loader warp fetches per batch
 constexpr float kActScale = 16.0f;                  // activations are stored as a * 2^4
+#ifndef CK_POLL_NS
+#define CK_POLL_NS 32
+#endif
+constexpr unsigned kPollNs = CK_POLL_NS;            // epilogue warps sleep this long between polls of the two accumulator barriers
 constexpr size_t kWtsBytes = (size_t)kG * 8192;     // [k-step][unit 4][co 128][16 B]
 // All CTAs stream the same 4.3 MB (L2-resident after the first tile pair).  kCopies > 1 replicates the
 // packed weights so that CTA b reads copy b % kCopies; measured no difference on B200 (the L2 serves the
@@ -261,7 +265,7 @@ tower_ts_kernel(const TowerParams prm) {
             int t = -1;
             if (ek0 < np && __any_sync(0xFFFFFFFFu, mbar_test(bar_acc_full(0), ph0))) t = 0;
             else if (ek1 < np && __any_sync(0xFFFFFFFFu, mbar_test(bar_acc_full(1), ph1))) t = 1;
-            if (t < 0) { __nanosleep(32); continue; }
+            if (t < 0) { __nanosleep(kPollNs); continue; }
             const int layer = t ? el1 : el0;
             const uint32_t k = t ? ek1 : ek0;
             if (t) ph1 ^= 1u; else ph0 ^= 1u;
