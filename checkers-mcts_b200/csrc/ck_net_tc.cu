@@ -1,4 +1,6 @@
-// ck_net_tc.cu -- K3 tower on 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+// ck_net_tc.cu -- K3 tower on 5th-gen tensor cores (tcgen05 + TMEM), sm_100a: the first, all-shared-memory
+// kernel (both MMA operands from shared memory, one tile per CTA).  Superseded as the product path by
+// ck_net_ts.cu (weights in TMEM, two tiles per CTA); kept as an independent cross-check (CK_TOWER=ss).
 //
 // All eight 3x3 convolutions of create_nn (reference training_pipeline.py:57-88: conv0..conv6
 // and the policy head's 3x3 conv; 98 % of the network's 134.87 MFLOP/position) run inside ONE
@@ -34,9 +36,12 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "ck_net.cuh"
+#include "ck_tc_ptx.cuh"
 
 namespace ck {
 namespace tc {
+
+using namespace ck::ptx;
 
 constexpr int kStageBytes = 32768;                 // 128 co x 64 ci x (hi + lo) fp16
 constexpr int kEpiWarps = 8;                        // two per TMEM lane quadrant, each takes half of the columns
@@ -63,66 +68,6 @@ template <int P, int S> struct Cfg {
     static constexpr int kBarOff = kActBytes + kStages * kStageBytes;
     static constexpr int kSmem = kBarOff + 256;
 };
-
-// ---- PTX wrappers --------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16, fp32 accumulate
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
-// [0,14) start>>4, [16,30) LBO>>4 (stride between the two 8-element K chunks of one MMA),
-// [32,46) SBO>>4 (stride between 8-row groups along M/N), [46,48) version = 1, layout_type 0.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 struct TowerParams {
     const ck_leaf *leaves;
@@ -172,11 +117,10 @@ tower_tc_kernel(const TowerParams prm) {
             for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
             mbar_init(bar_acc_full, 1);
             mbar_init(bar_act_ready, 32 * kEpiWarps);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_init_fence();
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(C::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc<C::kTmemCols>(smem_u32(s_tmem));
     }
     fence_proxy_async();
     tc_fence_before();
@@ -227,9 +171,9 @@ tower_tc_kernel(const TowerParams prm) {
                             const uint32_t b_addr = act_base + (chunk0 + 2 * ks) * C::kChunkStride + tap_off;
                             const uint64_t b_hi = make_desc(b_addr, C::kChunkStride, 160);
                             const uint64_t b_lo = make_desc(b_addr + C::kSplitBytes, C::kChunkStride, 160);
-                            tc_mma(tmem_base, a_hi, b_hi, C::kIdesc, (st | ks) != 0 ? 1u : 0u);
-                            tc_mma(tmem_base, a_hi, b_lo, C::kIdesc, 1u);
-                            tc_mma(tmem_base, a_lo, b_hi, C::kIdesc, 1u);
+                            tc_mma_ss(tmem_base, a_hi, b_hi, C::kIdesc, (st | ks) != 0 ? 1u : 0u);
+                            tc_mma_ss(tmem_base, a_hi, b_lo, C::kIdesc, 1u);
+                            tc_mma_ss(tmem_base, a_lo, b_hi, C::kIdesc, 1u);
                         }
                         tc_commit(bar_empty(slot));                                // frees the weight stage when the MMAs retire
                         if (st == ns - 1) tc_commit(bar_acc_full);                 // layer complete -> epilogue
@@ -335,7 +279,7 @@ tower_tc_kernel(const TowerParams prm) {
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+        tmem_dealloc<C::kTmemCols>(tmem_base);
     }
 }
 
