@@ -603,7 +603,13 @@ __device__ bool play_move(const WarpCtx &c) {
 }
 
 // ---- the per-round tree kernel ------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// CTAs per SM the register allocation is held to (95 registers, no spills).  Raising it to 6 or 7 fits the
+// whole cfg2 grid (1024 CTAs) in one wave at the price of spills; measured neutral to slightly negative in
+// steady state (3.74 / 3.73 / 3.72 / 3.70 M sims/s at 4 / 5 / 6 / 7), so the spill-free setting stays.
+#ifndef CK_TREE_OCC
+#define CK_TREE_OCC 5
+#endif
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, CK_TREE_OCC)
 tree_step_kernel(const EngineDev E) {
     __shared__ Slot s_slot[kWarpsPerBlock];
     __shared__ ck_pos s_kids[kWarpsPerBlock][CK_MAX_CHILDREN];
