@@ -305,13 +305,16 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
 }
 
 // ---- host side -----------------------------------------------------------------------------
-int net_reserve(ck_net *net, int64_t n) {
-    if (n <= net->cap) return CK_OK;
+// scratch between the tower and the heads: per position 64 + 1024 floats on the fused path (value conv
+// output; policy features + logits), two full fp32 feature maps [128][64] on the cross-check paths
+int net_reserve(ck_net *net, int64_t n, bool full_maps) {
+    const size_t per0 = full_maps ? (size_t)kC * 64 : 64, per1 = full_maps ? (size_t)kC * 64 : 1024;
+    if ((size_t)n * per0 <= net->act0_floats && (size_t)n * per1 <= net->act1_floats) return CK_OK;
     cudaFree(net->d_act0); cudaFree(net->d_act1);
-    net->d_act0 = net->d_act1 = nullptr; net->cap = 0;
-    CK_CUDA(cudaMalloc(&net->d_act0, (size_t)n * kC * 64 * sizeof(float)));
-    CK_CUDA(cudaMalloc(&net->d_act1, (size_t)n * kC * 64 * sizeof(float)));
-    net->cap = n;
+    net->d_act0 = net->d_act1 = nullptr; net->act0_floats = net->act1_floats = 0;
+    CK_CUDA(cudaMalloc(&net->d_act0, (size_t)n * per0 * sizeof(float)));
+    CK_CUDA(cudaMalloc(&net->d_act1, (size_t)n * per1 * sizeof(float)));
+    net->act0_floats = (size_t)n * per0; net->act1_floats = (size_t)n * per1;
     return CK_OK;
 }
 
@@ -351,7 +354,8 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
                      float *d_policy, float *d_value, cudaStream_t stream, int *launches) {
     if (!net->have_weights) return fail(CK_ERR_NO_NET, "ck_net: weights were never set");
     if (max_n <= 0) return CK_OK;
-    int rc = net_reserve(net, max_n);
+    static const bool tower_ss = [] { const char *v = getenv("CK_TOWER"); return v && v[0] == 's'; }();
+    int rc = net_reserve(net, max_n, net->impl == CK_NET_IMPL_SIMT || tower_ss);
     if (rc != CK_OK) return rc;
     rc = ensure_constants(net->device);
     if (rc != CK_OK) return rc;
@@ -381,7 +385,7 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
         CK_CUDA(cudaGetLastError());
     } else {
         // CK_TOWER=ss selects the earlier all-shared-memory tcgen05 kernel (cross-check)
-        static const bool use_ss = [] { const char *v = getenv("CK_TOWER"); return v && v[0] == 's'; }();
+        const bool use_ss = tower_ss;
         fused = !use_ss;
         // fused path: d_act0 receives the value conv1x1 output [n][64], d_act1 the policy features [n][512]
         rc = use_ss ? net_tc_tower(net, d_leaves, max_n, n_dev, trunk, pconv, stream, &nl)

@@ -35,8 +35,8 @@ struct ck_net {
     void *d_hpack = nullptr;         // policy Dense(512) weights, split fp16, UMMA layout (ck_heads_tc.cu)
     void *d_wts = nullptr;           // split-fp16 weights in k-step order for the weights-in-TMEM tower (ck_net_ts.cu)
     // activation scratch, grown on demand
-    int64_t cap = 0;
-    float *d_act0 = nullptr, *d_act1 = nullptr;   // [cap][128][64] fp32 (SIMT ping-pong / tower outputs)
+    size_t act0_floats = 0, act1_floats = 0;
+    float *d_act0 = nullptr, *d_act1 = nullptr;   // tower -> heads scratch (net_reserve)
     ck_leaf *d_leaves = nullptr;     // staging for host entry points
     float *d_policy = nullptr, *d_value = nullptr;
     int64_t io_cap = 0;
@@ -51,7 +51,7 @@ constexpr int kScaleVal1x1 = kScalePol1x1 + 16;       // 1 scale, 1 shift
 constexpr int kScaleValD1 = kScaleVal1x1 + 2;         // 64 scale, 64 shift
 constexpr int kScaleTotal = kScaleValD1 + 128;
 
-int net_reserve(ck_net *net, int64_t n);
+int net_reserve(ck_net *net, int64_t n, bool full_maps);
 // n_dev (optional): device pointer to the live row count; rows >= *n_dev are skipped
 int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
                      float *d_policy, float *d_value, cudaStream_t stream, int *launches);

@@ -70,6 +70,7 @@ struct TowerParams {
     const ck_leaf *leaves;
     const int32_t *n_dev;
     int32_t max_n;
+    int32_t tiles;               // 2: tiles X and Y per CTA; 1: X only (small batches: half the latency, twice the CTAs)
     const uint4 *wts;            // split-fp16 weights, k-step order
     const float *blob;           // Keras-ordered fp32 parameters (biases)
     const float *fold;           // folded BN scale/shift table
@@ -97,7 +98,8 @@ tower_ts_kernel(const TowerParams prm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n = prm.max_n;
     if (prm.n_dev != nullptr) n = min(n, *prm.n_dev);
-    const int n_pairs = (n + 2 * kP - 1) / (2 * kP);
+    const int ppi = prm.tiles * kP;                   // positions per CTA iteration
+    const int n_pairs = (n + ppi - 1) / ppi;
     if ((int)blockIdx.x >= n_pairs) return;
     const uint32_t np = (uint32_t)(n_pairs - 1 - (int)blockIdx.x) / gridDim.x + 1;   // tile pairs of this CTA
     const uint32_t total = np * (uint32_t)kG;                                        // k-steps this CTA streams
@@ -112,7 +114,7 @@ tower_ts_kernel(const TowerParams prm) {
     for (int i = tid * 16; i < 2 * kTileBytes; i += (int)blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
     if (warp == kMmaWarp0) {
         if (lane == 0) {
-            for (int s = 0; s < kNS; ++s) { mbar_init(bar_full(s), 4); mbar_init(bar_empty(s), 2); }
+            for (int s = 0; s < kNS; ++s) { mbar_init(bar_full(s), 4); mbar_init(bar_empty(s), (uint32_t)prm.tiles); }
             for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 32 * kEpiWarps); }
             mbar_init_fence();
             reinterpret_cast<int *>(smem + kVredOff + 2 * 4 * kN * 4)[0] = 0;
@@ -178,7 +180,7 @@ tower_ts_kernel(const TowerParams prm) {
         // trip count from kernel parameters and special registers only, so that the loop state (k-step
         // counter, descriptors, TMEM addresses) stays in uniform registers; the device-side batch count
         // only shortens the loop through the break below
-        const uint32_t npu = (uint32_t)((prm.max_n + 2 * kP - 1) / (2 * kP) - 1 - (int)blockIdx.x) / gridDim.x + 1;
+        const uint32_t npu = t < prm.tiles ? (uint32_t)((prm.max_n + ppi - 1) / ppi - 1 - (int)blockIdx.x) / gridDim.x + 1 : 0u;
         const uint32_t tile16 = (smem_u32(smem) + (uint32_t)(t * kTileBytes)) >> 4;      // tile base in 16-byte units
         constexpr uint32_t kDescLo = (uint32_t)(kChunkStride >> 4) << 16;                   // LBO
         constexpr uint64_t kDescHi = ((uint64_t)((160u >> 4) | (1u << 14))) << 32;          // SBO, descriptor version
@@ -220,7 +222,7 @@ tower_ts_kernel(const TowerParams prm) {
                 const int sq = et & 63, ch = (et >> 6) & 1, p = et >> 7, x = sq >> 3, y = sq & 7;
                 const bool dark = ((x ^ y) & 1) != 0;
                 const uint32_t bit = 1u << (4 * x + (y >> 1));
-                const int64_t pos = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * (2 * kP) + t * kP + p;
+                const int64_t pos = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * ppi + t * kP + p;
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -256,10 +258,10 @@ tower_ts_kernel(const TowerParams prm) {
         };
 
         build_input(0, 0);
-        build_input(1, 0);
+        if (prm.tiles > 1) build_input(1, 0);
         // per tile: next event = (pair ek, layer el), acc_full phase ph   (scalars: a runtime tile index
         // into arrays would put them in local memory)
-        uint32_t ek0 = 0u, ek1 = 0u, ph0 = 0u, ph1 = 0u;
+        uint32_t ek0 = 0u, ek1 = prm.tiles > 1 ? 0u : np, ph0 = 0u, ph1 = 0u;      // one tile: Y has no events
         int el0 = 0, el1 = 0;
         while (ek0 < np || ek1 < np) {
             int t = -1;
@@ -275,7 +277,7 @@ tower_ts_kernel(const TowerParams prm) {
             // fragment-layout load (thread: lanes t/4 and t/4+8, two adjacent squares), so that
             // stmatrix.trans can write whole 16-byte units (8 channels of one square) of the next
             // layer's operand: 8x fewer shared-memory store instructions than 2-byte stores.
-            const int64_t pos0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * (2 * kP) + t * kP;
+            const int64_t pos0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * ppi + t * kP;
             const float inv = prm.inv_scale[layer];
             const int t4 = lane >> 2, tq = lane & 3;
             uint32_t cur[32];
@@ -465,7 +467,7 @@ static int launch_tower_ts(ck_net *net, const ts::TowerParams &prm, int64_t max_
         CK_CUDA(cudaFuncSetAttribute(ts::tower_ts_kernel<kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmem));
         attr_done = true;
     }
-    const int64_t pairs = (max_n + 2 * ts::kP - 1) / (2 * ts::kP);
+    const int64_t pairs = (max_n + prm.tiles * ts::kP - 1) / (prm.tiles * ts::kP);
     const int grid = (int)std::min<int64_t>(pairs, num_sms(net->device));
     ts::tower_ts_kernel<kEpiWarps><<<grid, (ts::kLoaderWarps + 2 + kEpiWarps) * 32, ts::kSmem, stream>>>(prm);
     CK_CUDA(cudaGetLastError());
@@ -479,6 +481,10 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     const float *aux = (const float *)((const uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes);
     ts::TowerParams prm;
     prm.leaves = d_leaves; prm.n_dev = n_dev; prm.max_n = (int32_t)max_n;
+    // small batches (arena, tournaments, a few hundred self-play games): one tile per CTA fills twice as many
+    // SMs and halves the latency of the launch; from two positions per SM on, two tiles share the weight stream
+    static const int force_tiles = [] { const char *v = getenv("CK_TS_TILES"); return v ? atoi(v) : 0; }();
+    prm.tiles = force_tiles == 1 || force_tiles == 2 ? force_tiles : (max_n <= (int64_t)ts::kP * num_sms(net->device) ? 1 : 2);
     prm.wts = (const uint4 *)net->d_wts; prm.blob = net->d_blob; prm.fold = net->d_scale;
     prm.inv_scale = aux + 16;
     prm.plane5 = aux + 32;

@@ -418,7 +418,7 @@ def test_selfplay_with_network(lib):
     net.close()
 
 
-@pytest.mark.parametrize("tower", ["ts", "ss"])
+@pytest.mark.parametrize("tower", ["ts", "ts-one-tile", "ts-two-tiles", "ss"])
 def test_tower_kernels_agree_with_fp32_path(tower):
     """both tcgen05 towers (weights-in-TMEM product kernel, shared-memory cross-check) against the fp32
     CUDA-core path on ragged batch sizes: single tile pair, odd tails, the persistent multi-pair loop.
@@ -426,7 +426,11 @@ def test_tower_kernels_agree_with_fp32_path(tower):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CK_TOWER=tower)
+    env = dict(os.environ, CK_TOWER=tower[:2])
+    if tower == "ts-one-tile":
+        env["CK_TS_TILES"] = "1"          # small-batch mode forced on every size (the default picks it up to 296)
+    elif tower == "ts-two-tiles":
+        env["CK_TS_TILES"] = "2"
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_tower.py"), "1", "2", "3", "5", "97", "593", "1187", "4099"],
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
