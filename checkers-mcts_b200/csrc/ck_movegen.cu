@@ -49,33 +49,54 @@ movegen_kernel(const uint4 *__restrict__ pos, int64_t n, int max_children, ck_po
 // ---- K1, packed output -------------------------------------------------------------------
 // Same successors as movegen_kernel, written back to back (CSR): the children of position i are
 // children[offsets[i] .. offsets[i+1]) in the reference's list order.  The strided [n][max_children]
-// layout touches 768 B of address space per position to store ~70 B, which is what kept K1 at 15 % of
-// the HBM roofline; here the kernel moves the algorithmic bytes only (16 B in, 4 B offset, 32 B mask,
-// 2 B status/plane5 and 16 B per child out).  One pass: tiles of 256 positions take a ticket, scan
-// their counts (warp shuffles + shared memory) and chain the tile totals with a decoupled look-back
-// over 64-bit {flag, value} words, so offsets are deterministic and no second sweep is needed.
-constexpr int kCsrTile = 256;
-constexpr unsigned long long kCsrAgg = 1ull << 62, kCsrIncl = 2ull << 62, kCsrVal = (1ull << 62) - 1;
+// layout touches 768 B of address space per position to store ~70 B; here the kernels move the
+// algorithmic bytes only (16 B in, 4 B offset, 32 B mask, 2 B status/plane5 and 16 B per child out).
+// Two launches on the caller's stream:
+//   count  thread per position: legal-action planes, status, plane5, and the tile's (256 positions)
+//          successor count; the last tile to finish scans the tile counts into tile bases (offsets[n] = total)
+//   emit   tile: positions again (L2 hits), block scan -> offsets, a (square, direction, owner) byte list of
+//          the tile's moves in the reference's order; then ONE LANE PER SUCCESSOR builds it with
+//          make_child_fast.  Every lane does the same work and consecutive lanes store consecutive 16-byte
+//          successors (one lane per position ran its piece x direction loops around the full successor
+//          construction with 11.6 of 32 lanes active and scattered its stores).
+// (A single-pass variant that chained the tiles with a decoupled look-back was latency-bound: with
+// 256-position tiles ~1200 tiles are in flight and each walked ~37 predecessor probes.)
+constexpr int kCsrTile = 256;                        // positions per tile; owner indices are stored in one byte
+static_assert(kCsrTile <= 256, "s_owner holds the position index of a move in a uint8_t");
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp_tot, uint32_t *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp_tot[w] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < kCsrTile / 32; ++q) {
+        const uint32_t u = s_warp_tot[q];
+        if (q < w) warp_off += u;
+        tot += u;
+    }
+    *total = tot;
+    return warp_off + incl - v;
+}
 
 __global__ void __launch_bounds__(kCsrTile)
-movegen_csr_kernel(const uint4 *__restrict__ pos, int64_t n, ck_pos *__restrict__ children, uint32_t child_cap,
-                   uint32_t *__restrict__ offsets, uint4 *__restrict__ masks, uint8_t *__restrict__ status,
-                   uint8_t *__restrict__ plane5, unsigned int *__restrict__ ticket, unsigned long long *__restrict__ tile_state) {
-    __shared__ unsigned int s_tile;
+movegen_count_kernel(const uint4 *__restrict__ pos, int64_t n, uint4 *__restrict__ masks, uint8_t *__restrict__ status,
+                     uint8_t *__restrict__ plane5, uint32_t *__restrict__ tile_tot, unsigned int *__restrict__ done,
+                     uint32_t *__restrict__ total_out) {
     __shared__ uint32_t s_warp_tot[kCsrTile / 32];
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);          // tiles are chained in ticket order: every predecessor is already running
-    __syncthreads();
-    const unsigned int tile = s_tile;
-    const int64_t i = (int64_t)tile * kCsrTile + tid;
-    ck_pos p;
-    p.p1 = p.p2 = p.k = p.meta = 0;
-    uint32_t mask[8];
+    const int64_t i = (int64_t)blockIdx.x * kCsrTile + threadIdx.x;
     int cnt = 0;
     if (i < n) {
         const uint4 v = __ldg(pos + i);
+        ck_pos p;
         p.p1 = v.x; p.p2 = v.y; p.k = v.z; p.meta = v.w;
+        uint32_t mask[8];
         cnt = gen_moves(p, NullSink{}, mask);
         int p5;
         const int st = outcome_of(p, cnt > 0, &p5);
@@ -86,58 +107,95 @@ movegen_csr_kernel(const uint4 *__restrict__ pos, int64_t n, ck_pos *__restrict_
         if (status) status[i] = (uint8_t)st;
         if (plane5) plane5[i] = (uint8_t)p5;
     }
-    // exclusive scan of the counts inside the tile
-    uint32_t incl = (uint32_t)cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp_tot[w] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0, tile_total = 0;
-#pragma unroll
-    for (int q = 0; q < kCsrTile / 32; ++q) {
-        const uint32_t v = s_warp_tot[q];
-        if (q < w) warp_off += v;
-        tile_total += v;
-    }
-    const uint32_t loc = warp_off + incl - (uint32_t)cnt;
-    // chain the tile totals (decoupled look-back, one warp, 32 predecessors per probe)
-    if (w == 0) {
-        unsigned long long base = 0;
-        if (lane == 0) atomicExch(tile_state + tile, (tile == 0 ? kCsrIncl : kCsrAgg) | tile_total);
-        if (tile > 0) {
-            int64_t look = (int64_t)tile - 1;
-            for (;;) {
-                const int64_t idx = look - lane;
-                unsigned long long v = kCsrIncl;                       // before tile 0: inclusive prefix 0
-                if (idx >= 0) v = *reinterpret_cast<volatile unsigned long long *>(tile_state + idx);
-                if (__any_sync(0xFFFFFFFFu, (v >> 62) == 0)) continue; // a predecessor has not published yet
-                const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-                const int first = incl_mask ? __ffs((int)incl_mask) - 1 : 31;
-                unsigned long long part = lane <= first ? (v & kCsrVal) : 0ull;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-                base += part;
-                if (incl_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) atomicExch(tile_state + tile, kCsrIncl | (base + tile_total));
-        }
-        if (lane == 0) {
-            s_base = base;
-            if ((int64_t)(tile + 1) * kCsrTile >= n && offsets) offsets[n] = (uint32_t)(base + tile_total);
-        }
+    uint32_t total;
+    block_exclusive_scan((uint32_t)cnt, s_warp_tot, &total);
+    // the last tile to finish turns the tile counts into tile bases (exclusive scan) for the emit launch
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        tile_tot[blockIdx.x] = total;
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    const unsigned long long off = s_base + loc;
+    if (!s_last) return;
+    __threadfence();
+    uint32_t carry = 0;
+    for (int64_t b = 0; b < (int64_t)gridDim.x; b += kCsrTile) {
+        const int64_t j = b + threadIdx.x;
+        const uint32_t v = j < (int64_t)gridDim.x ? *(volatile uint32_t *)(tile_tot + j) : 0u;
+        __syncthreads();                                  // s_warp_tot is reused
+        uint32_t tot;
+        const uint32_t ex = block_exclusive_scan(v, s_warp_tot, &tot);
+        if (j < (int64_t)gridDim.x) tile_tot[j] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        if (total_out) *total_out = carry;
+        *done = 0u;                                       // ready for the next call
+    }
+}
+
+__global__ void __launch_bounds__(kCsrTile)
+movegen_emit_kernel(const uint4 *__restrict__ pos, int64_t n, ck_pos *__restrict__ children, uint32_t child_cap,
+                    uint32_t *__restrict__ offsets, const uint32_t *__restrict__ tile_base) {
+    __shared__ uint32_t s_warp_tot[kCsrTile / 32];
+    __shared__ uint4 s_pos[kCsrTile], s_hop[kCsrTile];    // position; its hop sets (make_child_fast)
+    __shared__ uint32_t s_off[kCsrTile];                  // first successor inside the tile | jump flag << 31
+    __shared__ uint8_t s_move[kCsrTile * CK_MAX_CHILDREN]; // the tile's move list: source square | direction << 5
+    __shared__ uint8_t s_owner[kCsrTile * CK_MAX_CHILDREN]; // and the position (thread) each move belongs to
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kCsrTile + tid;
+    ck_pos p;
+    p.p1 = p.p2 = p.k = p.meta = 0;
+    uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
     if (i < n) {
-        if (offsets) offsets[i] = (uint32_t)off;
-        if (children != nullptr && cnt > 0) {
-            const int room = off >= child_cap ? 0 : (int)min((unsigned long long)cnt, (unsigned long long)child_cap - off);
-            if (room > 0) gen_moves(p, ArraySink{children + off, room}, mask);
+        const uint4 v = __ldg(pos + i);
+        p.p1 = v.x; p.p2 = v.y; p.k = v.z; p.meta = v.w;
+        cnt = gen_moves(p, NullSink{}, mask);
+    }
+    uint32_t tile_total;
+    const uint32_t loc = block_exclusive_scan((uint32_t)cnt, s_warp_tot, &tile_total);
+    const uint32_t base = tile_base[blockIdx.x];
+    if (i < n && offsets) offsets[i] = base + loc;
+    if (children == nullptr) return;
+    {
+        // per position: the (square, direction) list in the reference's order -- a few instructions per
+        // move, so the divergence of this loop is cheap; the heavy part (building the successor) runs
+        // below with one lane per successor
+        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+        const Side sd = side_of(p);
+        uint32_t J[4];
+        hop_sets(sd, J);
+        s_pos[tid] = make_uint4(p.p1, p.p2, p.k, p.meta);
+        s_hop[tid] = make_uint4(J[0], J[1], J[2], J[3]);
+        s_off[tid] = loc | (jump ? 0x80000000u : 0u);
+        const uint32_t u0 = jump ? mask[4] : mask[0], u1 = jump ? mask[5] : mask[1], u2 = jump ? mask[6] : mask[2], u3 = jump ? mask[7] : mask[3];
+        const uint32_t any = u0 | u1 | u2 | u3;
+        uint32_t m = loc;
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool king = pass == 1;
+            for (uint32_t rem = any & (king ? sd.kings : ~sd.kings); rem; rem &= rem - 1) {
+                const int s = ffs32(rem);
+                const int nd = king ? 4 : 2;
+                for (int q = 0; q < nd; ++q) {
+                    const int d = order_dir(king, jump, sd.player, q);
+                    const uint32_t ud = d == 0 ? u0 : d == 1 ? u1 : d == 2 ? u2 : u3;       // selects, not an indexed (local-memory) array
+                    if ((ud >> s) & 1u) { s_move[m] = (uint8_t)(s | (d << 5)); s_owner[m] = (uint8_t)tid; ++m; }
+                }
+            }
         }
+    }
+    __syncthreads();
+    for (uint32_t c = tid; c < tile_total; c += kCsrTile) {
+        const int lo = s_owner[c];
+        const uint4 pv = s_pos[lo], hv = s_hop[lo];
+        ck_pos par;
+        par.p1 = pv.x; par.p2 = pv.y; par.k = pv.z; par.meta = pv.w;
+        const uint32_t J[4] = {hv.x, hv.y, hv.z, hv.w};
+        const uint32_t mv = s_move[c];
+        const ck_pos ch = make_child_fast(par, side_of(par), J, (int)(mv & 31u), (int)(mv >> 5), (s_off[lo] >> 31) != 0);
+        if ((unsigned long long)base + c < child_cap) reinterpret_cast<uint4 *>(children)[base + c] = make_uint4(ch.p1, ch.p2, ch.k, ch.meta);
     }
 }
 
@@ -237,17 +295,22 @@ int ck_movegen_csr_device(const ck_pos *d_pos, int64_t n, ck_pos *d_children, in
         return CK_OK;
     }
     const int64_t tiles = (n + kCsrTile - 1) / kCsrTile;
-    const size_t need = 16 + (size_t)tiles * sizeof(unsigned long long);      // [ticket, pad][tile states]
+    const size_t need = (size_t)(tiles + 2) * sizeof(uint32_t);               // [tile counts -> bases][total][arrival counter]
     if (g_csr_ws_bytes[dev] < need) {
         CK_CUDA(cudaDeviceSynchronize());
         cudaFree(g_csr_ws[dev]); g_csr_ws[dev] = nullptr; g_csr_ws_bytes[dev] = 0;
-        CK_CUDA(cudaMalloc(&g_csr_ws[dev], need));
-        g_csr_ws_bytes[dev] = need;
+        const size_t room = need * 2;
+        CK_CUDA(cudaMalloc(&g_csr_ws[dev], room));
+        CK_CUDA(cudaMemset(g_csr_ws[dev], 0, room));                          // the counter resets itself after every call
+        g_csr_ws_bytes[dev] = room;
     }
-    CK_CUDA(cudaMemsetAsync(g_csr_ws[dev], 0, need, (cudaStream_t)stream));
-    movegen_csr_kernel<<<(unsigned)tiles, kCsrTile, 0, (cudaStream_t)stream>>>(
-        (const uint4 *)d_pos, n, d_children, (uint32_t)child_cap, d_offsets, (uint4 *)d_masks, d_status, d_plane5,
-        (unsigned int *)g_csr_ws[dev], (unsigned long long *)((uint8_t *)g_csr_ws[dev] + 16));
+    // the counter sits at a fixed place (the end of the allocation) so that calls with different n share it
+    uint32_t *tile_tot = (uint32_t *)g_csr_ws[dev];
+    unsigned int *done = (unsigned int *)((uint8_t *)g_csr_ws[dev] + g_csr_ws_bytes[dev] - sizeof(unsigned int));
+    cudaStream_t st = (cudaStream_t)stream;
+    movegen_count_kernel<<<(unsigned)tiles, kCsrTile, 0, st>>>((const uint4 *)d_pos, n, (uint4 *)d_masks, d_status, d_plane5, tile_tot, done,
+                                                              d_offsets ? d_offsets + n : tile_tot + tiles);
+    movegen_emit_kernel<<<(unsigned)tiles, kCsrTile, 0, st>>>((const uint4 *)d_pos, n, d_children, (uint32_t)child_cap, d_offsets, tile_tot);
     CK_CUDA(cudaGetLastError());
     return CK_OK;
 }

@@ -163,6 +163,53 @@ CK_HD ck_pos make_child(const ck_pos &par, const Side &sd, int s, int d, bool ju
     return c;
 }
 
+// squares from which a hop in direction e is geometrically possible on this board: an opponent piece next
+// door and an empty landing square behind it (whoever stands on the square)
+CK_HD void hop_sets(const Side &sd, uint32_t J[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) J[e] = nb_in(e, sd.opp) & land_in(e, sd.empty);
+}
+
+// make_child with the per-position work hoisted out: J = hop_sets(parent).  Same result as make_child;
+// index arithmetic on the 32-square board instead of (x, y) coordinates, and the "can the hopping piece hop
+// again" test (stale parent emptiness, child opponents, Checkers.py:225-237, 279-281) reduced to bit tests:
+// removing the captured piece only changes the hop set of the direction that points back at it.
+CK_HD ck_pos make_child_fast(const ck_pos &par, const Side &sd, const uint32_t J[4], int s, int d, bool jump) {
+    const int x = s >> 2, odd = x & 1;
+    const int md = (d == 0 ? -4 : d == 1 ? -3 : d == 2 ? 4 : 5) - odd;      // one diagonal step from an even / odd row
+    const int jd = d == 0 ? -9 : d == 1 ? -7 : d == 2 ? 7 : 9;              // two steps
+    const int t = s + (jump ? jd : md);
+    const uint32_t sb = 1u << s, tb = 1u << t;
+    const bool king = (sd.kings >> s) & 1u;
+    uint32_t own = (sd.own ^ sb) | tb, opp = sd.opp, kings = sd.kings & ~sb;
+    if (jump) {
+        const uint32_t mb = 1u << (s + md);
+        opp &= ~mb;
+        kings &= ~mb;
+    }
+    const int tx = t >> 2;
+    const bool kinged = !king && (sd.player == 0 ? tx == 7 : tx == 0);
+    if (king || kinged) kings |= tb;
+    int next_player = 1 - sd.player;
+    if (jump && !kinged) {
+        uint32_t again = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool allowed = king || (sd.player == 0 ? e >= 2 : e < 2);
+            if (allowed && e != 3 - d) again |= (J[e] >> t) & 1u;
+        }
+        if (again) next_player = sd.player;
+    }
+    ck_pos c;
+    c.p1 = sd.player == 0 ? own : opp;
+    c.p2 = sd.player == 0 ? opp : own;
+    c.k = kings;
+    const int action = ((jump ? 4 : 0) + d) * 64 + 2 * s + (odd ^ 1);       // x*8 + y = 2s + (row even)
+    const int rev = (king && !jump) ? meta_rev(par.meta) + 1 : 0;
+    c.meta = make_meta(next_player, rev, action, 1, meta_ply(par.meta) + 1);
+    return c;
+}
+
 CK_HD bool any_legal(const Side &sd) {
     const DirSets D = dir_sets(sd.own, sd.opp, sd.kings, sd.empty, sd.empty, sd.player);
     return (D.mv[0] | D.mv[1] | D.mv[2] | D.mv[3] | D.jp[0] | D.jp[1] | D.jp[2] | D.jp[3]) != 0;
@@ -242,6 +289,53 @@ CK_HD int gen_moves(const ck_pos &p, const Sink &sink, uint32_t mask[8]) {
         }
     }
     return total;
+}
+
+// Random access into the list gen_moves produces: the k-th successor (0 <= k < count) without
+// materialising the others.  `use` are the per-direction source sets (= the legal-action planes:
+// mask[0..3] for plain moves, mask[4..7] for jumps).  The list order is men in ascending square order
+// with their two forward directions in order_dir order, then kings likewise with four directions, so
+// the square is found by a five-step search over prefix popcounts.  Used by the packed movegen kernel,
+// where one lane per SUCCESSOR (instead of per position) keeps warps converged and stores coalesced.
+CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, int k) {
+    const Side sd = side_of(p);
+    const uint32_t kings = sd.kings;
+    const int da = order_dir(false, jump, sd.player, 0), db = order_dir(false, jump, sd.player, 1);
+    const uint32_t ua = use[da] & ~kings, ub = use[db] & ~kings;
+    const int men_total = popc32(ua) + popc32(ub);
+    int s = 0, d;
+    if (k < men_total) {
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const uint32_t below = (1u << (s + step)) - 1u;
+            if (popc32(ua & below) + popc32(ub & below) <= k) s += step;
+        }
+        const uint32_t below = (1u << s) - 1u;
+        const int r = k - popc32(ua & below) - popc32(ub & below);
+        d = (r == 0 && ((ua >> s) & 1u)) ? da : db;
+    } else {
+        k -= men_total;
+        uint32_t uk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) uk[i] = use[order_dir(true, jump, sd.player, i)] & kings;
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const uint32_t below = (1u << (s + step)) - 1u;
+            if (popc32(uk[0] & below) + popc32(uk[1] & below) + popc32(uk[2] & below) + popc32(uk[3] & below) <= k) s += step;
+        }
+        const uint32_t below = (1u << s) - 1u;
+        int r = k - popc32(uk[0] & below) - popc32(uk[1] & below) - popc32(uk[2] & below) - popc32(uk[3] & below);
+        d = order_dir(true, jump, sd.player, 3);
+#pragma unroll
+        for (int i = 2; i >= 0; --i) {
+            // number of this king's directions before slot i
+            int before = 0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (q < i) before += (int)((uk[q] >> s) & 1u);
+            if (((uk[i] >> s) & 1u) && before == r) d = order_dir(true, jump, sd.player, i);
+        }
+    }
+    return make_child(p, sd, s, d, jump);
 }
 
 CK_HD ck_pos start_position() {

@@ -25,6 +25,10 @@ def hr():
     L.ckh_movegen.argtypes = [C.POINTER(O.Pos), C.POINTER(O.Pos), C.POINTER(C.c_uint32),
                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ckh_movegen.restype = C.c_int
+    L.ckh_movegen_fast.argtypes = [C.POINTER(O.Pos), C.POINTER(O.Pos)]
+    L.ckh_movegen_fast.restype = C.c_int
+    L.ckh_kth.argtypes = [C.POINTER(O.Pos), C.c_int, C.POINTER(O.Pos)]
+    L.ckh_kth.restype = None
     L.ckh_status.argtypes = [C.POINTER(O.Pos), C.POINTER(C.c_int)]
     L.ckh_status.restype = C.c_int
     return L
@@ -36,6 +40,13 @@ def _host_movegen(L, pos):
     st, p5 = C.c_int(), C.c_int()
     p = O.Pos(*[int(v) for v in pos])
     n = L.ckh_movegen(C.byref(p), ch, mask, C.byref(st), C.byref(p5))
+    one = O.Pos()
+    for k in range(n):                                   # random access must agree with the generated list
+        L.ckh_kth(C.byref(p), k, C.byref(one))
+        assert one.tup() == ch[k].tup(), (pos, k)
+    fast = (O.Pos * O.MAX_CHILDREN)()                     # the packed kernel's lean successor construction
+    assert L.ckh_movegen_fast(C.byref(p), fast) == n
+    assert [fast[i].tup() for i in range(n)] == [ch[i].tup() for i in range(n)], pos
     p5b = C.c_int()
     st2 = L.ckh_status(C.byref(p), C.byref(p5b))
     assert (st2, p5b.value) == (st.value, p5.value)
