@@ -106,7 +106,6 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
 struct WarpCtx {
     const EngineDev &E;
     Slot &S;                 // shared-memory copy of the slot
-    ck_pos *kids;            // shared, CK_MAX_CHILDREN entries
     uint32_t *path;          // global, kMaxDepth entries
     ck_pos *hist;            // global, max_plies + 1 entries
     int slot, lane;
@@ -282,13 +281,15 @@ __device__ void expand_pending(const WarpCtx &c) {
     const int t = S.cur, leaf = S.pend_leaf, net = S.pend_net;
     uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
     const ck_pos lp = to_pos(pos[leaf]);
+    // every lane derives the legal-action planes itself (a few dozen bit operations); the successors are
+    // then built one per lane (kth_move + make_child_fast) instead of serially by lane 0
     uint32_t mask[8];
-    int b = 0;
-    if (c.lane == 0) b = gen_moves(lp, ArraySink{c.kids, CK_MAX_CHILDREN}, mask);
-    b = __shfl_sync(CK_FULL, b, 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) mask[i] = __shfl_sync(CK_FULL, mask[i], 0);
-    __syncwarp();
+    const int b = gen_moves(lp, NullSink{}, mask);
+    const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+    const uint32_t use[4] = {jump ? mask[4] : mask[0], jump ? mask[5] : mask[1], jump ? mask[6] : mask[2], jump ? mask[7] : mask[3]};
+    const Side lsd = side_of(lp);
+    uint32_t hop[4];
+    hop_sets(lsd, hop);
     const float *prow = E.policy[net] + (int64_t)S.pend_row * CK_POLICY_SIZE;
     float masked[16];
     const float psum = masked_policy_sum(prow, mask, c.lane, masked);
@@ -302,7 +303,9 @@ __device__ void expand_pending(const WarpCtx &c) {
     }
     const int lplayer = meta_player(lp.meta);
     for (int i = c.lane; i < b; i += 32) {
-        const ck_pos ch = c.kids[b - 1 - i];            // node.children = legal list reversed (:72-75)
+        int ms, md;
+        kth_move(lsd, use, jump, b - 1 - i, &ms, &md);                     // node.children = legal list reversed (:72-75)
+        const ck_pos ch = make_child_fast(lp, lsd, hop, ms, md, jump);
         int p5;
         const int stc = status_of(ch, &p5);
         const float prior = __fdiv_rn(prow[meta_action(ch.meta)], psum);
@@ -618,7 +621,6 @@ __device__ bool play_move(const WarpCtx &c) {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, CK_TREE_OCC)
 tree_step_kernel(const EngineDev E) {
     __shared__ Slot s_slot[kWarpsPerBlock];
-    __shared__ ck_pos s_kids[kWarpsPerBlock][CK_MAX_CHILDREN];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * kWarpsPerBlock + w;
     if (slot >= E.n_slots) return;
@@ -629,7 +631,7 @@ tree_step_kernel(const EngineDev E) {
         for (int i = lane; i < (int)(sizeof(Slot) / 4); i += 32) dst[i] = src[i];
     }
     __syncwarp();
-    WarpCtx c{E, S, s_kids[w], E.path + (int64_t)slot * kMaxDepth, E.hist + (int64_t)slot * (E.max_plies + 1), slot, lane};
+    WarpCtx c{E, S, E.path + (int64_t)slot * kMaxDepth, E.hist + (int64_t)slot * (E.max_plies + 1), slot, lane};
     bool live = true;
     if (E.ctr->error != 0) live = false;
     if (live && S.game < 0) live = S.manual ? false : refill(c);

@@ -297,8 +297,8 @@ CK_HD int gen_moves(const ck_pos &p, const Sink &sink, uint32_t mask[8]) {
 // with their two forward directions in order_dir order, then kings likewise with four directions, so
 // the square is found by a five-step search over prefix popcounts.  Used by the packed movegen kernel,
 // where one lane per SUCCESSOR (instead of per position) keeps warps converged and stores coalesced.
-CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, int k) {
-    const Side sd = side_of(p);
+// (source square, direction) of the k-th entry of that list
+CK_HD void kth_move(const Side &sd, const uint32_t use[4], bool jump, int k, int *s_out, int *d_out) {
     const uint32_t kings = sd.kings;
     const int da = order_dir(false, jump, sd.player, 0), db = order_dir(false, jump, sd.player, 1);
     const uint32_t ua = use[da] & ~kings, ub = use[db] & ~kings;
@@ -335,6 +335,12 @@ CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, in
             if (((uk[i] >> s) & 1u) && before == r) d = order_dir(true, jump, sd.player, i);
         }
     }
+    *s_out = s; *d_out = d;
+}
+CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, int k) {
+    const Side sd = side_of(p);
+    int s, d;
+    kth_move(sd, use, jump, k, &s, &d);
     return make_child(p, sd, s, d, jump);
 }
 
