@@ -1,31 +1,36 @@
-// ck_net_ts.cu -- K3 tower, weights-in-TMEM variant (tcgen05.mma with the A operand in tensor
-// memory), sm_100a.  The product path of ck_net_forward*/the engine; ck_net_tc.cu keeps the
-// earlier all-shared-memory kernel as a cross-check (CK_TOWER=ss).
+// ck_net_ts.cu -- K3 tower, weights-in-TMEM kernel (tcgen05.mma with the A operand in tensor memory),
+// sm_100a.  The product path of ck_net_forward* and of the engine; ck_net_tc.cu keeps the earlier
+// all-shared-memory kernel as a cross-check (CK_TOWER=ss).
 //
-// Same arithmetic contract as ck_net_tc.cu: the eight 3x3 convolutions of create_nn (reference
-// training_pipeline.py:57-88) as D[co][square] = sum_k W[co][k] * act[k][square] with split-fp16
-// operands (Whi*Ahi + Whi*Alo + Wlo*Ahi, fp32 accumulation in TMEM), epilogue = bias + ReLU +
-// folded BatchNorm (conv -> bias -> ReLU -> BN, :60-63).  What changed is where the operands live
-// and how the layer-to-layer dependency is hidden:
+// Nine GEMM layers per position without leaving the SM: the eight 3x3 convolutions of create_nn (reference
+// training_pipeline.py:57-88) and the policy head's 1x1 convolution (:89-96), each as
+// D[co][square] = sum_k W[co][k] * act[k][square] with split-fp16 operands (Whi*Ahi + Whi*Alo + Wlo*Ahi,
+// fp32 accumulation in TMEM) and the epilogue bias + ReLU + folded BatchNorm (conv -> bias -> ReLU -> BN,
+// :60-63); the value head's 1x1 convolution (:102-105) is reduced in the conv6 epilogue.  Outputs per
+// position: pflat[512] (policy features, flattened in (x, y, c) order) and vconv[64].
 //
-//   * WEIGHTS never touch shared memory.  Four loader warps stream the pre-packed split-fp16
-//     weights from L2 with coalesced 16-byte loads (one output channel = one TMEM lane per
-//     thread) and write them with tcgen05.st into a 16-slot ring of TMEM columns [256,512)
-//     (one slot = one k-step = 16 input channels of one tap: 8 columns hi + 8 columns lo).
-//     The MMAs take A from TMEM, so shared-memory bandwidth is spent on the activation (B) operand
-//     only (64 B/clk instead of > 128 B/clk for an N = 128 tile with both operands in smem).
-//   * TWO position tiles (X, Y; 2 positions = N 128 each, accumulators in TMEM columns [0,128)
-//     and [128,256)) share every weight slot.  Y runs kSkew k-steps behind X, so when X finishes
-//     a layer its epilogue overlaps Y's remaining MMAs and then X's next layer overlaps Y's
-//     epilogue: the tensor pipe does not idle across the layer boundary, which was the 17 % +
-//     exposed epilogue of the single-tile kernel (profiles/r1c_tower_ncu_summary.json).
-//   * Activations: shared memory, split fp16 (hi, lo), zero-padded 10 x 10 boards in the UMMA
-//     K-major no-swizzle core-matrix layout with rows interleaved over the 2 positions of a tile
-//     (byte offset = chunk(ci/8)*kChunkStride + ((2*row + p)*10 + col)*16 + (ci%8)*2), so a 3x3 tap
-//     is a descriptor start offset and one MMA covers the whole tile.  2 tiles x 100.5 KB.
-//   * Warp roles: warps 0-3 weight loaders (TMEM lane quadrant = warp), warps 4..4+E-1 epilogue
-//     (quadrant = warp % 4, E/4 warps share a quadrant's columns), last warp MMA issuer + TMEM
-//     allocator.  mbarriers: full/empty per weight slot, acc_full / act_ready per tile.
+//   * WEIGHTS never touch shared memory.  Eight loader warps (two sets of four, one warp per TMEM lane
+//     quadrant) stream the pre-packed split-fp16 weights from L2 with coalesced 16-byte loads (one output
+//     channel = one TMEM lane per thread) and write them with tcgen05.st into a 16-slot ring of TMEM
+//     columns [256,512) (one slot = one k-step = 16 input channels of one tap: 8 columns hi + 8 lo).  The
+//     MMAs take A from TMEM, so shared-memory bandwidth is spent on the activation (B) operand only
+//     (64 B/clk instead of 128 B/clk for an N = 128 tile with both operands in shared memory).
+//   * TWO position tiles (X, Y; 2 positions = N 128 each, accumulators in TMEM columns [0,128) and
+//     [128,256)) share every weight slot, each with its own MMA-issuing warp.  The issuers are not ordered
+//     against each other: while one tile is in its epilogue the other owns the tensor pipe, and the ring
+//     bounds how far they drift apart.  A single tile leaves the pipe idle during every epilogue (17 % of the
+//     earlier kernel, profiles/r1c_tower_ncu_summary.json).  Small batches run with one tile per CTA
+//     (TowerParams::tiles) to fill twice as many SMs.
+//   * Activations: shared memory, split fp16 (hi, lo), zero-padded 10 x 10 boards in the UMMA K-major
+//     no-swizzle core-matrix layout with rows interleaved over the 2 positions of a tile
+//     (byte offset = chunk(ci/8)*kChunkStride + ((2*row + p)*10 + col)*16 + (ci%8)*2), so a 3x3 tap is a
+//     descriptor start offset and one MMA covers the whole tile.  2 tiles x 100.5 KB.
+//   * Epilogue: 8 warps (quadrant = warp % 4, two warps share a quadrant's columns) poll both accumulators;
+//     tcgen05.ld.16x256b gives the mma-fragment layout, stmatrix.trans writes whole 16-byte operand units.
+//   * Warp roles: warps 0-7 loaders, 8-15 epilogue, 16-17 MMA issuers (16 also allocates TMEM).
+//     mbarriers: full/empty per weight slot, acc_full / act_ready per tile.
+// Tried and measured neutral (kept out): replicating the weights per CTA group, longer epilogue poll sleeps,
+// 16 epilogue warps, splitting act_ready so the next layer starts on the first half of the channels.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "ck_net.cuh"
@@ -492,8 +497,6 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     prm.bias_off[8] = L.pol1x1.bias;
     prm.val1x1_k = L.val1x1.kernel; prm.val1x1_b = L.val1x1.bias;
     prm.pflat = d_pflat; prm.vconv = d_vconv;
-    static const int variant = [] { const char *v = getenv("CK_TS_VARIANT"); return v ? atoi(v) : 0; }();
-    (void)variant;
     const int rc = launch_tower_ts<8>(net, prm, max_n, stream);
     if (rc != CK_OK) return rc;
     if (launches) *launches += 1;
