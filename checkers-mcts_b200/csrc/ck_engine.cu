@@ -727,7 +727,8 @@ struct ck_engine {
     EngineDev dev;           // device pointers + config, passed by value to the kernels
     ck_net *net[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream_b = nullptr;    // arena: the second network evaluates next to the first one
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> prof_ev;   // 3 per round in profile mode: before eval, after tower, after eval
     std::vector<char> fetched;          // per local game: records already handed out by ck_records_fetch_new
     Counters *h_ctr = nullptr;        // pinned
@@ -745,6 +746,9 @@ static void engine_free(ck_engine *e) {
     for (int k = 0; k < 2; ++k) { cudaFree(d.leaves[k]); cudaFree(d.policy[k]); cudaFree(d.value[k]); }
     cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half);
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
+    if (e->stream_b) cudaStreamDestroy(e->stream_b);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
@@ -800,6 +804,11 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     if (cfg->keep_records) d.max_rec = (cfg->terminate_cnt > 0 ? cfg->terminate_cnt : d.max_plies) + 1;
     CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK_E(cudaEventCreate(&e->ev0)); CK_E(cudaEventCreate(&e->ev1));
+    if (cfg->arena) {
+        CK_E(cudaStreamCreateWithFlags(&e->stream_b, cudaStreamNonBlocking));
+        CK_E(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        CK_E(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
     const size_t nodes = (size_t)d.n_slots * 3 * d.cap;
     CK_E(cudaMalloc(&d.pos, nodes * sizeof(uint4)));
     CK_E(cudaMalloc(&d.stat, nodes * sizeof(uint4)));
@@ -896,16 +905,28 @@ int ck_engine_begin(ck_engine *e, int64_t n_games) {
 
 static int engine_eval(ck_engine *e, int *launches) {
     EngineDev &d = e->dev;
+    // arena: the two networks' batches are independent (each at most half of the slots), so the second one
+    // is evaluated on its own stream and its CTAs run on the SMs the first launch leaves idle
+    const bool fork = d.cfg.arena && e->stream_b != nullptr && e->net[0] != e->net[1];     // one net object = one scratch area
+    if (fork) {
+        CK_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+        CK_CUDA(cudaStreamWaitEvent(e->stream_b, e->ev_fork, 0));
+    }
     for (int k = 0; k < (d.cfg.arena ? 2 : 1); ++k) {
+        cudaStream_t st = (fork && k == 1) ? e->stream_b : e->stream;
         int kind = d.cfg.evaluator;
         if (k == 1 && d.cfg.evaluator_p2 >= 0) kind = d.cfg.evaluator_p2;
         if (kind == CK_EVAL_NET) {
-            int rc = net_forward_rows(e->net[k], d.leaves[k], d.n_slots, &d.ctr->batch_count[k], d.policy[k], d.value[k], e->stream, launches);
+            int rc = net_forward_rows(e->net[k], d.leaves[k], d.n_slots, &d.ctr->batch_count[k], d.policy[k], d.value[k], st, launches);
             if (rc != CK_OK) return rc;
         } else {
-            stub_eval_kernel<<<(d.n_slots * 32 + 127) / 128, 128, 0, e->stream>>>(d.leaves[k], &d.ctr->batch_count[k], kind, d.policy[k], d.value[k]);
+            stub_eval_kernel<<<(d.n_slots * 32 + 127) / 128, 128, 0, st>>>(d.leaves[k], &d.ctr->batch_count[k], kind, d.policy[k], d.value[k]);
             if (launches) *launches += 1;
         }
+    }
+    if (fork) {
+        CK_CUDA(cudaEventRecord(e->ev_join, e->stream_b));
+        CK_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     }
     return CK_OK;
 }
