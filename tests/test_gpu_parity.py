@@ -435,3 +435,39 @@ def test_tower_kernels_agree_with_fp32_path(tower):
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count(" ok ") == 8 and "MISMATCH" not in r.stdout
+
+
+def test_full_size_properties_and_batch_independence(lib):
+    """cfg2 size (4096 concurrent games, 400 sims/move) with the network evaluator, noise and temperature on:
+    (i) structural invariants of every record, (ii) the run is reproducible bit for bit although leaves
+    get their batch rows in a different (atomic) order every time -- i.e. a position's evaluation does not
+    depend on its row, its tile mates or the CTA that processed it, (iii) a game's records do not depend on
+    how many games run next to it (the same game ids in a 592-slot and in a 128-slot engine)."""
+    from ckb200 import net as N
+    net = lib.Net(0)
+    net.set_weights(N.random_init_blob(0))
+
+    def run(slots):
+        eng = lib.Engine(lib.make_cfg(n_slots=slots, budget=400, training=True, terminate_cnt=3, evaluator="net", keep_records=True,
+                                      uct_c=4.0, alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=99))
+        eng.set_net(0, net)
+        st = eng.selfplay(slots)                     # every game: three searched moves, then the ply-cap adjudication
+        recs = eng.records()
+        eng.close()
+        return st, recs[np.lexsort((recs["ply"], recs["game"]))]
+
+    st, a = run(4096)
+    assert st["games_finished"] == 4096 and len(a) == 3 * 4096 and st["moves"] == 3 * 4096
+    assert st["nn_evals"] <= st["sims"] and st["sims"] >= 3 * 400 * 4096
+    n = a["n_children"].astype(np.int64)
+    vis = a["visits"].astype(np.int64)
+    col = np.arange(vis.shape[1])[None, :]
+    assert (np.where(col < n[:, None], vis, 0).sum(1) == a["root_n"].astype(np.int64) - 1).all()      # :433-434
+    assert (a["root_n"] >= 400).all() and (np.abs(a["q"]) <= 1).all() and (np.abs(a["z"]) <= 1).all()
+    st2, b = run(4096)
+    assert st2["sims"] == st["sims"] and a.tobytes() == b.tobytes()
+    _st3, c = run(592)
+    assert len(c) == 3 * 592 and a[a["game"] < 592].tobytes() == c.tobytes()
+    _st4, d = run(128)                              # small batch: the tower runs one tile per CTA
+    assert len(d) == 3 * 128 and a[a["game"] < 128].tobytes() == d.tobytes()
+    net.close()
