@@ -892,6 +892,8 @@ int ck_engine_begin(ck_engine *e, int64_t n_games) {
         e->rec_cap = (size_t)n_games * d.max_rec;
     }
     CK_CUDA(cudaMemsetAsync(d.results, 0xFF, (size_t)n_games * sizeof(ck_game_result), e->stream));
+    // records are handed out whole: entries of action[] / visits[] beyond n_children must read as zero
+    if (d.cfg.keep_records) CK_CUDA(cudaMemsetAsync(d.rec, 0, (size_t)n_games * d.max_rec * sizeof(ck_record), e->stream));
     d.n_games = (int32_t)n_games;
     const int stride = d.cfg.game_id_stride ? d.cfg.game_id_stride : 1;
     d.arena_half = (int32_t)((n_games * stride) / 2);
