@@ -11,7 +11,9 @@
 // in TMEM): the activation chunk is converted from fp32 by the CTA's threads straight into the UMMA
 // K-major core-matrix layout, the pre-packed weight chunk (64 KB, hi + lo) arrives by one bulk copy.
 // The fp32 CUDA-core version (heads_kernel) needs ~35 us of FMA issue for a 4096-position batch and
-// measured 86 us; this one is bounded by moving 8 MB of pflat + 8 MB of logits.
+// measured 86 us; this one takes 25 us and is latency-bound (tensor pipe 10 % active: each CTA waits for its
+// activation rows chunk by chunk; a two-stage version that converts chunk k+1 while chunk k multiplies
+// measured the same, the loads would have to be prefetched deeper).
 // heads_finish_kernel: one warp per position, softmax over the 512 logits and the value head tail.
 #include <cuda_fp16.h>
 #include "ck_net.cuh"
@@ -228,10 +230,10 @@ int net_heads_tc(ck_net *net, const float *d_pflat, const float *d_vconv, float 
                  float *d_policy, float *d_value, cudaStream_t stream, int *launches) {
     if (!net->d_hpack) return fail(CK_ERR_NO_NET, "tensor-core heads: weights were never packed");
     const NetLayout L = net_layout();
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};          // per device: function attributes belong to the context
+    if (!attr_done[net->device & 63]) {
         CK_CUDA(cudaFuncSetAttribute(htc::heads_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, htc::kSmem));
-        attr_done = true;
+        attr_done[net->device & 63] = true;
     }
     const float *aux = (const float *)((const uint8_t *)net->d_hpack + htc::kPackBytes);
     const dim3 grid((unsigned)((max_n + htc::kM - 1) / htc::kM), 4);

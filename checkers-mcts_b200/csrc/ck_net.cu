@@ -365,11 +365,11 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
     int nl = 0;
     bool fused = false;
     if (net->impl == CK_NET_IMPL_SIMT) {
-        static bool attr_done = false;
+        static bool attr_done[64] = {false};      // per device: function attributes belong to the context
         const int smem128 = kC * kPlaneStride * sizeof(float), smem14 = 14 * kPlaneStride * sizeof(float);
-        if (!attr_done) {
+        if (!attr_done[net->device & 63]) {
             CK_CUDA(cudaFuncSetAttribute(conv3x3_simt_kernel<kC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));
-            attr_done = true;
+            attr_done[net->device & 63] = true;
         }
         float *a = net->d_act0, *b = net->d_act1;
         conv3x3_simt_kernel<14, true><<<(unsigned)max_n, 256, smem14, stream>>>(
@@ -395,11 +395,11 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
     if (net->ev_after_tower) CK_CUDA(cudaEventRecord(net->ev_after_tower, stream));
     HeadParams hp{L.pol1x1.kernel, L.pol1x1.bias, L.pol_dense_k, L.pol_dense_b, L.val1x1.kernel, L.val1x1.bias,
                   L.val_d1_k, L.val_d1_b, L.val_d2_k, L.val_d2_b};
-    static bool heads_attr_done = false;
-    if (!heads_attr_done) {
+    static bool heads_attr_done[64] = {false};
+    if (!heads_attr_done[net->device & 63]) {
         CK_CUDA(cudaFuncSetAttribute(heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
         CK_CUDA(cudaFuncSetAttribute(heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
-        heads_attr_done = true;
+        heads_attr_done[net->device & 63] = true;
     }
     const unsigned hgrid = (unsigned)((max_n + kHeadPB - 1) / kHeadPB);
     // CK_HEADS=simt keeps the fp32 CUDA-core Dense for the fused path too (cross-check)

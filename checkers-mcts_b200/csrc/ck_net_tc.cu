@@ -370,11 +370,11 @@ int net_tc_prepare(ck_net *net) {
 
 template <int P, int S>
 static int launch_tower(ck_net *net, const tc::TowerParams &prm, int64_t max_n, cudaStream_t stream) {
-    static bool attr_done = false;
+    static bool attr_done[64] = {false};          // per device (and per template instantiation)
     static_assert(tc::Cfg<P, S>::kSmem <= 232448, "tower tile does not fit in shared memory");
-    if (!attr_done) {
+    if (!attr_done[net->device & 63]) {
         CK_CUDA(cudaFuncSetAttribute(tc::tower_tc_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<P, S>::kSmem));
-        attr_done = true;
+        attr_done[net->device & 63] = true;
     }
     const int64_t tiles = (max_n + P - 1) / P;
     const int grid = (int)std::min<int64_t>(tiles, num_sms(net->device));

@@ -466,11 +466,11 @@ int net_ts_prepare(ck_net *net) {
 
 template <int kEpiWarps>
 static int launch_tower_ts(ck_net *net, const ts::TowerParams &prm, int64_t max_n, cudaStream_t stream) {
-    static bool attr_done = false;
+    static bool attr_done[64] = {false};          // per device (and per template instantiation)
     static_assert(ts::kSmem <= 232448, "tower tiles do not fit in shared memory");
-    if (!attr_done) {
+    if (!attr_done[net->device & 63]) {
         CK_CUDA(cudaFuncSetAttribute(ts::tower_ts_kernel<kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmem));
-        attr_done = true;
+        attr_done[net->device & 63] = true;
     }
     const int64_t pairs = (max_n + prm.tiles * ts::kP - 1) / (prm.tiles * ts::kP);
     const int grid = (int)std::min<int64_t>(pairs, num_sms(net->device));
