@@ -14,10 +14,12 @@ from ckb200 import net as N  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 max_term = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+pool_cap = int(os.environ.get("LR_POOL_CAP", "0"))
+eps = float(os.environ.get("LR_EPS", "0.25"))
 net = L.Net(0)
 net.set_weights(N.random_init_blob(0))
 eng = L.Engine(L.make_cfg(n_slots=4096, budget=400, training=True, terminate_cnt=200, evaluator="net", keep_records=True,
-                          uct_c=4.0, alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=20261017,
+                          uct_c=4.0, alpha=1.0, epsilon=eps, tau=1.0, pool_cap=pool_cap, tau_decay=0.1, tau_decay_delay=10, seed=20261017,
                           max_terminal_sims_per_step=max_term))
 eng.set_net(0, net)
 eng.begin(4096 * 8)
