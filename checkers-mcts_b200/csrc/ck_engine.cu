@@ -154,15 +154,16 @@ __device__ void backup(const WarpCtx &c, int depth, bool is_outcome, int outcome
 
 // Marsaglia-Tsang gamma(alpha) from Philox words (np.random.dirichlet, MCTS.py:108);
 // statistical parity only (SURVEY 8b RNG row)
+// Exp(1) from one random word.  A 24-bit uniform and a single-precision logarithm are ample for exploration
+// noise (the sum that enters PUCT is formed in float64 as in the reference); the float64 log was a third of
+// the instructions of a descent.
+__device__ __forceinline__ double exp1_from(uint32_t w) {
+    return (double)(-logf((float)((w >> 8) + 1u) * (1.0f / 16777216.0f)));
+}
+
 __device__ double gamma_sample(const Philox &rng, uint32_t c0, uint32_t c1, uint32_t c2, double alpha) {
     uint32_t r[4];
-    if (alpha == 1.0) {
-        // Gamma(1) = Exp(1).  A 24-bit uniform and a single-precision logarithm are ample for exploration
-        // noise (the sum that enters PUCT is formed in float64 as in the reference); the float64 log was a
-        // third of the instructions of a descent.
-        rng(c0, c1, c2, 0x44495231u, r);
-        return (double)(-logf((float)((r[0] >> 8) + 1u) * (1.0f / 16777216.0f)));
-    }
+    if (alpha == 1.0) { rng(c0, c1, c2, 0x44495231u, r); return exp1_from(r[0]); }
     const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
     const double d = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
     double out = d;
@@ -201,6 +202,7 @@ __device__ int select_leaf(const WarpCtx &c, int *out_depth) {
     const uint4 *stat = c.stat_of(t);
     const Philox rng(game_key(E, c.S.game));
     int node = c.S.root[t], depth = 0;
+    uint32_t noise_a[4] = {0u, 0u, 0u, 0u};
     if (c.lane == 0) c.path[0] = (uint32_t)node;
     uint4 st = stat[node];
     for (;;) {
@@ -215,8 +217,21 @@ __device__ int select_leaf(const WarpCtx &c, int *out_depth) {
         double n0 = 0.0, n1 = 0.0;
         if (E.cfg.epsilon != 0.0) {                      // fresh Dirichlet(alpha) at every node, every visit (:107-108)
             const uint32_t cc0 = (uint32_t)c.S.search_id, cc1 = (uint32_t)c.S.sims_done;
-            const double g0 = c.lane < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | c.lane), E.cfg.alpha) : 0.0;
-            const double g1 = c.lane + 32 < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), E.cfg.alpha) : 0.0;
+            double g0, g1 = 0.0;
+            if (E.cfg.alpha == 1.0) {
+                // Gamma(1) = Exp(1): one Philox block (four words) serves a child slot for four consecutive
+                // levels of the descent -- word depth & 3 of the block keyed by (search, simulation, depth / 4, child)
+                if ((depth & 3) == 0) {
+                    rng(cc0, cc1, (uint32_t)((depth >> 2) << 8 | c.lane), 0x44495231u, noise_a);
+                }
+                const uint32_t w = (depth & 2) ? ((depth & 1) ? noise_a[3] : noise_a[2]) : ((depth & 1) ? noise_a[1] : noise_a[0]);
+                g0 = c.lane < b ? exp1_from(w) : 0.0;
+                // more than 32 children is rare: those slots draw their own block per level
+                if (c.lane + 32 < b) g1 = gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), 1.0);
+            } else {
+                g0 = c.lane < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | c.lane), E.cfg.alpha) : 0.0;
+                g1 = c.lane + 32 < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), E.cfg.alpha) : 0.0;
+            }
             double tot = g0 + g1;
 #pragma unroll
             for (int o = 16; o; o >>= 1) tot += shfl_xor_d(tot, o);
