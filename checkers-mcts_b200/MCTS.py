@@ -1,7 +1,8 @@
 """Drop-in for the reference's ``MCTS`` / ``MCTS_Node`` (reference MCTS.py:36-430) on top of the
 device engine.  The whole tree lives in GPU memory (structure-of-arrays node pool, libckb200
 ``ck_tree_*`` entry points); ``MCTS_Node`` objects are thin views that fetch ``n / w / p`` and
-their children lazily.  Class-level configuration, method names, argument meaning and raised
+their children lazily.  Each root built with ``MCTS_Node(state)`` starts its own device tree, so the
+reference's one-tree-per-player game loops (play_Checkers.py:128-157) run unchanged.  Class-level configuration, method names, argument meaning and raised
 errors follow the reference:
 
     MCTS(GAME_ENV=..., UCT_C=..., CONSTRAINT='rollout', BUDGET=..., MULTIPROC=False, NEURAL_NET=True,
@@ -26,10 +27,28 @@ from ckb200 import lib as _L
 from Checkers import history_counters
 
 
+class _Tree(object):
+    """One search tree in GPU memory: a single-slot engine (``ck_tree_*`` entry points use slot 0)."""
+
+    def __init__(self, engine, net, kind):
+        self.engine, self.net, self.kind = engine, net, kind
+        self.epoch = 0               # engine.tree_epoch() the node ids of this tree's views belong to
+        self.root_idx = None
+        self.closed = False
+
+    def close(self):
+        if not self.closed:
+            self.closed = True
+            self.engine.close()
+
+
 class MCTS(object):
-    _engine = None
-    _generation = 0          # bumped whenever the device tree is rebuilt from scratch
-    _root_idx = None
+    # The reference keeps one Python tree per player (play_Checkers.py:128-157, training_pipeline.py:353-377)
+    # and a tournament game two more; the least recently created device tree is dropped beyond this many.
+    max_trees = 4
+    _trees = []
+    _tree_serial = 0         # every tree draws from its own random stream
+    engine_options = {}      # extra ckb200.lib.make_cfg arguments (pool_cap, compact_always, ...)
 
     @classmethod
     def __init__(cls, **kwargs):
@@ -47,24 +66,24 @@ class MCTS(object):
         cls.tau_decay = kwargs['TEMPERATURE_DECAY']
         cls.tau_decay_delay = kwargs['TEMP_DECAY_DELAY']
         cls.seed = kwargs.get('SEED', 1)
+        cls.engine_options = dict(kwargs.get('ENGINE_OPTIONS', {}))
         if cls.constraint != 'rollout':
             raise ValueError('Invalid MCTS computational constraint!' if cls.constraint != 'time' else
                              "CONSTRAINT='time' is not supported by the device engine; use 'rollout'")
         if not cls.neural_net:
             raise ValueError('NEURAL_NET=False (random rollouts) is served by ckb200.lib.rollout, not by MCTS')
-        cls._close_engine()
+        cls._close_trees()
 
     # ---- engine plumbing ---------------------------------------------------------------------
     @classmethod
-    def _close_engine(cls):
-        if cls._engine is not None:
-            cls._engine.close()
-            cls._engine = None
+    def _close_trees(cls):
+        for tree in cls._trees:
+            tree.close()
+        cls._trees = []
 
     @classmethod
-    def _ensure_engine(cls):
-        if cls._engine is not None:
-            return cls._engine
+    def _new_tree(cls):
+        """a fresh device tree configured from the class-level search parameters"""
         net = getattr(cls.game_env, 'neural_net', None)
         kind = getattr(net, 'ck_evaluator', None)
         device = getattr(cls.game_env, 'device', 0)
@@ -73,12 +92,16 @@ class MCTS(object):
                             'ckb200.net.StubNet; the search runs on the GPU and cannot call a host predict()')
         cfg = _L.make_cfg(n_slots=1, budget=cls.budget, device=device, uct_c=cls.uct_c, training=cls.training,
                           alpha=cls.alpha, epsilon=cls.epsilon, tau=cls.tau, tau_decay=cls.tau_decay,
-                          tau_decay_delay=cls.tau_decay_delay, evaluator=kind, keep_records=False, seed=cls.seed)
-        cls._engine = _L.Engine(cfg)
+                          tau_decay_delay=cls.tau_decay_delay, evaluator=kind, keep_records=False,
+                          seed=(cls.seed + 0x9E3779B97F4A7C15 * cls._tree_serial) % (1 << 63), **cls.engine_options)
+        cls._tree_serial += 1
+        tree = _Tree(_L.Engine(cfg), net, kind)
         if kind == "net":
-            cls._engine.set_net(0, net.net)
-        cls._net_in_engine = net
-        return cls._engine
+            tree.engine.set_net(0, net.net)
+        while len(cls._trees) >= cls.max_trees:
+            cls._trees.pop(0).close()
+        cls._trees.append(tree)
+        return tree
 
     # ---- reference API -----------------------------------------------------------------------
     @classmethod
@@ -98,21 +121,32 @@ class MCTS(object):
         """BUDGET new simulations from ``root_node`` on top of any inherited statistics
         (MCTS.py:210-224)."""
         start = datetime.now()
-        if getattr(cls, '_net_in_engine', None) is not getattr(cls.game_env, 'neural_net', None):
-            cls._close_engine()                      # the caller swapped game_env.neural_net (tournaments do)
-        eng = cls._ensure_engine()
-        if root_node._generation != cls._generation or root_node._idx is None:
-            # a node that is not part of the device tree: start a fresh tree at its state
+        net = getattr(cls.game_env, 'neural_net', None)
+        tree = root_node._tree
+        if tree is not None and not tree.closed and tree.kind == "net" and tree.net is not net \
+                and getattr(net, 'ck_evaluator', None) == "net":
+            tree.engine.set_net(0, net.net)          # the caller swapped game_env.neural_net (tournaments do)
+            tree.net = net
+        if tree is None or tree.closed or root_node._idx is None or root_node._epoch != tree.epoch \
+                or tree.kind != getattr(net, 'ck_evaluator', None):
+            # a node that is not part of a live device tree: start a fresh tree at its state
+            tree = cls._new_tree()
             rev, ply = history_counters(root_node.history)
             pos = codec.encode_state(root_node.state, rev, ply)
             hist = cls.game_env.history
             parent_player = int(hist[-2][4, 0, 0]) if len(hist) >= 2 else -1    # MCTS.py:167-173
-            eng.tree_set_root(pos, parent_player)
-            cls._generation += 1
-            root_node._generation, root_node._idx = cls._generation, 0           # a fresh root is node 0
-        elif root_node._idx != cls._root_idx:
-            eng.tree_reroot(root_node._idx)
-        cls._root_idx = root_node._idx
+            tree.engine.tree_set_root(pos, parent_player)
+            root_node._tree, root_node._idx, root_node._epoch = tree, 0, tree.epoch   # a fresh root is node 0
+        elif root_node._idx != tree.root_idx:
+            tree.engine.tree_reroot(root_node._idx)
+            epoch = tree.engine.tree_epoch()
+            if epoch != tree.epoch:
+                # the engine compacted the tree around the new root: it is node 0 now and every
+                # other view of this tree is stale
+                tree.epoch = epoch
+                root_node._idx, root_node._epoch = 0, epoch
+        tree.root_idx = root_node._idx
+        eng = tree.engine
         if cls.verbose:
             print('Starting search!')
         eng.tree_search(cls.budget)
@@ -200,8 +234,9 @@ class MCTS_Node(object):
         self._number_of_visits = 0
         self._total_reward = 0
         self._prior_prob = 0
-        self._idx = None                 # node id inside the device tree (-1: its root at creation)
-        self._generation = -1
+        self._tree = None                # device tree this view belongs to
+        self._idx = None                 # node id inside that tree
+        self._epoch = -1                 # tree epoch the id is valid for
         self._status = None
         self.printed = False
 
@@ -210,8 +245,9 @@ class MCTS_Node(object):
     def children(self):
         if self._children is None:
             self._children = []
-            if self._idx is not None and self._generation == MCTS._generation and MCTS._engine is not None:
-                for c in MCTS._engine.tree_children(self._idx):
+            tree = self._tree
+            if tree is not None and not tree.closed and self._idx is not None and self._epoch == tree.epoch:
+                for c in tree.engine.tree_children(self._idx):
                     node = MCTS_Node.__new__(MCTS_Node)
                     node.state = codec.decode_state(c["pos"])
                     node.player = MCTS.current_player(node.state)
@@ -220,7 +256,7 @@ class MCTS_Node(object):
                     node.depth = self.depth + 1
                     node._children = None
                     node._number_of_visits, node._total_reward, node._prior_prob = c["n"], c["w"], c["p"]
-                    node._idx, node._generation, node._status = c["idx"], self._generation, c["terminal"]
+                    node._tree, node._idx, node._epoch, node._status = tree, c["idx"], self._epoch, c["terminal"]
                     node.printed = False
                     self._children.append(node)
         return self._children

@@ -103,6 +103,8 @@ def _load():
     L.ck_tree_advance.argtypes = [vp, i32]
     L.ck_tree_node_count.argtypes = [vp]
     L.ck_tree_node_count.restype = i64
+    L.ck_tree_epoch.argtypes = [vp]
+    L.ck_tree_epoch.restype = i64
     return L
 
 
@@ -350,6 +352,9 @@ class Engine(object):
 
     def tree_node_count(self):
         return int(_lib.ck_tree_node_count(self._h))
+
+    def tree_epoch(self):
+        return int(_lib.ck_tree_epoch(self._h))
 
     def close(self):
         if self._h:

@@ -680,6 +680,25 @@ tree_step_kernel(const EngineDev E) {
     }
 }
 
+// single-search API: renumber slot 0's current tree around its root (ck_tree_reroot when the pool runs short)
+__global__ void __launch_bounds__(32) manual_compact_kernel(const EngineDev E) {
+    __shared__ Slot S;
+    const int lane = threadIdx.x;
+    {
+        const int *src = reinterpret_cast<const int *>(E.slots);
+        int *dst = reinterpret_cast<int *>(&S);
+        for (int i = lane; i < (int)(sizeof(Slot) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    WarpCtx c{E, S, E.path, E.hist, 0, lane};
+    compact_tree(c, S.cur, S.root[S.cur]);
+    {
+        int *dst = reinterpret_cast<int *>(E.slots);
+        const int *src = reinterpret_cast<const int *>(&S);
+        for (int i = lane; i < (int)(sizeof(Slot) / 4); i += 32) dst[i] = src[i];
+    }
+}
+
 // simulation / evaluation totals live per slot (no hot-path atomics); summed on demand
 __global__ void sum_slots_kernel(const EngineDev E, unsigned long long *out_sims, unsigned long long *out_evals) {
     unsigned long long s = 0, e = 0;
@@ -747,11 +766,13 @@ struct ck_engine {
     std::vector<cudaEvent_t> prof_ev;   // 3 per round in profile mode: before eval, after tower, after eval
     std::vector<char> fetched;          // per local game: records already handed out by ck_records_fetch_new
     Counters *h_ctr = nullptr;        // pinned
+    unsigned long long *d_tot = nullptr;   // ck_engine_run: simulation / evaluation totals before and after
     int64_t n_games = 0;
     size_t rec_cap = 0, res_cap = 0;
     bool profile = false;
     bool begun = false;
     uint64_t total_steps = 0;
+    int64_t tree_epoch = 0;             // single-search API: times the node ids were renumbered
 };
 
 static void engine_free(ck_engine *e) {
@@ -759,7 +780,7 @@ static void engine_free(ck_engine *e) {
     EngineDev &d = e->dev;
     cudaFree(d.pos); cudaFree(d.stat); cudaFree(d.hist); cudaFree(d.path); cudaFree(d.slots); cudaFree(d.ctr);
     for (int k = 0; k < 2; ++k) { cudaFree(d.leaves[k]); cudaFree(d.policy[k]); cudaFree(d.value[k]); }
-    cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half);
+    cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half); cudaFree(e->d_tot);
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->stream_b) cudaStreamDestroy(e->stream_b);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -838,6 +859,7 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         CK_E(cudaMalloc(&d.value[k], (size_t)d.n_slots * sizeof(float)));
     }
     CK_E(cudaMallocHost(&e->h_ctr, sizeof(Counters)));
+    CK_E(cudaMalloc(&e->d_tot, 4 * sizeof(unsigned long long)));
     {
         // node.n ** 0.5 is libm pow in the reference (MCTS.py:110) and differs from sqrt for
         // some integers; the table is built with the host's libm so the two agree.
@@ -976,8 +998,7 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
     int rc = engine_poll(e);
     if (rc != CK_OK) return rc;
     const Counters before = *e->h_ctr;
-    unsigned long long *d_tot = nullptr;
-    CK_CUDA(cudaMalloc(&d_tot, 4 * sizeof(unsigned long long)));
+    unsigned long long *d_tot = e->d_tot;
     CK_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), e->stream));
     sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot, d_tot + 1);
     int launches = 0;
@@ -999,16 +1020,16 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
                 if (e->net[0]) e->net[0]->ev_after_tower = e->prof_ev[3 * i + 1];
                 rc = engine_eval(e, &launches);
                 if (e->net[0]) e->net[0]->ev_after_tower = nullptr;
-                if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+                if (rc != CK_OK) return rc;
                 CK_CUDA(cudaEventRecord(e->prof_ev[3 * i + 2], e->stream));
             } else {
                 rc = engine_round(e, &launches);
-                if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+                if (rc != CK_OK) return rc;
             }
         }
         steps += chunk;
         rc = engine_poll(e);
-        if (rc != CK_OK) { cudaFree(d_tot); return rc; }
+        if (rc != CK_OK) return rc;
         if (e->profile) {
             for (int64_t i = 0; i < chunk; ++i) {
                 float a = 0.f, b = 0.f;
@@ -1027,7 +1048,6 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
     unsigned long long tot[4];
     CK_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, e->stream));
     CK_CUDA(cudaStreamSynchronize(e->stream));
-    cudaFree(d_tot);
     e->total_steps += (uint64_t)steps;
     if (stats) {
         float ms = 0.f;
@@ -1186,6 +1206,7 @@ int ck_tree_search(ck_engine *e, int32_t sims) {
     int rc = manual_slot(e, &s);
     if (rc != CK_OK) return rc;
     s.manual_target = sims; s.sims_done = 0;       // BUDGET new simulations on top of inherited statistics (MCTS.py:217)
+    s.search_id += 1;                              // a new search draws new exploration noise
     if (s.phase == PH_HALT) s.phase = PH_SEARCH;
     CK_CUDA(cudaMemcpy(d.slots, &s, sizeof(Slot), cudaMemcpyHostToDevice));
     for (;;) {
@@ -1275,8 +1296,18 @@ int ck_tree_reroot(ck_engine *e, int32_t node) {
     s.root[s.cur] = node;
     s.phase = PH_HALT; s.sims_done = 0;
     CK_CUDA(cudaMemcpy(d.slots, &s, sizeof(Slot), cudaMemcpyHostToDevice));
+    if (d.cap - s.alloc[s.cur] < d.compact_need || d.cfg.compact_always) {
+        // not enough room for another search: keep the subtree under the new root only.  Node ids change
+        // (the root becomes node 0); ck_tree_epoch tells the caller that ids it holds are stale.
+        manual_compact_kernel<<<1, 32, 0, e->stream>>>(d);
+        CK_CUDA(cudaGetLastError());
+        CK_CUDA(cudaStreamSynchronize(e->stream));
+        e->tree_epoch += 1;
+    }
     return CK_OK;
 }
+
+int64_t ck_tree_epoch(ck_engine *e) { return e ? e->tree_epoch : -1; }
 
 int ck_tree_advance(ck_engine *e, int32_t child_index) {
     int32_t idx[CK_MAX_CHILDREN], b = 0;

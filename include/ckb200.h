@@ -213,8 +213,13 @@ int ck_tree_root_children(ck_engine *, ck_pos *pos, uint32_t *n, float *w, float
 int ck_tree_children(ck_engine *, int32_t node, int32_t *idx, ck_pos *pos, uint32_t *n, float *w, float *p,
                      int32_t *status, int32_t *count);
 int ck_tree_best_child(ck_engine *, int32_t move_count, int32_t *index);
-/* make `node` (an id from ck_tree_children) the root of the same tree (MCTS.new_root_node) */
+/* make `node` (an id from ck_tree_children) the root of the same tree (MCTS.new_root_node).  When the
+ * node pool cannot hold another search the subtree under the new root is compacted: the root becomes
+ * node 0, every other id changes and ck_tree_epoch() advances by one. */
 int ck_tree_reroot(ck_engine *, int32_t node);
+/* number of times ck_tree_reroot has renumbered the tree; ids from ck_tree_children are valid only
+ * while this value is unchanged */
+int64_t ck_tree_epoch(ck_engine *);
 /* re-root on the child with this index (MCTS.new_root_node for a one-ply advance) */
 int ck_tree_advance(ck_engine *, int32_t child_index);
 int64_t ck_tree_node_count(ck_engine *);

@@ -99,6 +99,48 @@ def test_mcts_shim_first_search_and_reroot(mods):
         M.MCTS.begin_tree_search(M.MCTS_Node(env3.state))
 
 
+def _action(state):
+    return (int(state[14, 0, 0]) - 6) * 64 + int(state[14, 0, 1]) * 8 + int(state[14, 0, 2])
+
+
+@pytest.mark.parametrize("engine_options", [{}, {"compact_always": True}], ids=["default", "compact-every-reroot"])
+def test_play_loop_two_trees_matches_reference_game(mods, engine_options):
+    """play_Checkers' game loop (one tree per player, re-rooted through the opponent's reply) through the MCTS /
+    MCTS_Node views: root and child statistics of every search equal the reference's own game
+    (mcts_kat.json: _generate_data run verbatim, two trees, 40 plies), also when the device tree is
+    renumbered at every re-rooting."""
+    import play_Checkers as P
+    from ckb200.net import StubNet
+    kat = json.load(open(os.path.join(GOLDEN, "mcts_kat.json")))["hash_game"]
+    log = []
+
+    def spy(root, best):
+        log.append((root.n, float(root.w), [(_action(c.state), c.n, float(c.w), float(c.p), bool(c.terminal))
+                                             for c in root.children], [int(v) for v in best.state[14, 0, 0:3]]))
+
+    kw = dict(MCTS_KW, BUDGET=kat["budget"], TRAINING=True, ENGINE_OPTIONS=engine_options)
+    outcome, plies = P.play(StubNet("hash"), kw, max_plies=kat["terminate_cnt"], quiet=True, on_search=spy)
+    assert plies == kat["terminate_cnt"] and len(log) == len(kat["moves"]) and outcome is None
+    for i, (got, want) in enumerate(zip(log, kat["moves"])):
+        assert got[0] == want["root_n"] and got[1] == want["root_w"], i
+        assert got[2] == [(c["action"], c["n"], c["w"], c["p"], c["terminal"]) for c in want["children"]], i
+    assert [g[3] for g in log[:len(kat["chosen"])]] == kat["chosen"]
+    assert len(mods[1].MCTS._trees) == 2                       # one device tree per player
+
+
+def test_play_loop_human_input(mods, capsys):
+    import play_Checkers as P
+    from ckb200.net import StubNet
+    answers = iter(["99", "1", "2", "1", "1", "1", "1"])
+    outcome, plies = P.play(StubNet("uniform_material"), dict(MCTS_KW, BUDGET=30), human_player2=True, max_plies=6,
+                            print_trees=True, tree_depth=1, input_fn=lambda prompt: next(answers))
+    out = capsys.readouterr().out
+    assert plies == 6 and outcome is None
+    assert 'Invalid selection!  Try again!' in out and 'Option #1: (' in out and '|- (' in out
+    env = mods[0].Checkers(StubNet("hash"))
+    assert P.states_to_piece_positions(env.state, env.legal_next_states)[0] == [(3, 2), (4, 3)]
+
+
 def test_generate_data_pickle_matches_reference_golden(mods, tmp_path, monkeypatch):
     _, _, T = mods
     f = np.load(os.path.join(GOLDEN, "selfplay_hash.npz"))
