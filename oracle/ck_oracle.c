@@ -382,6 +382,8 @@ static double rng_gamma(rng_t *r, double a) {       /* Marsaglia-Tsang */
 /* ------------------------------------------------------------------------------------
  * MCTS tree: MCTS_Node (MCTS.py:345-430) and MCTS class methods (:59-295)
  * ---------------------------------------------------------------------------------- */
+static uint64_t splitmix64(uint64_t *x);
+
 typedef struct node {
     cko_pos pos;
     uint32_t mask[8];
@@ -404,6 +406,7 @@ struct cko_tree {
     double *tau_ref;
     cko_eval_fn eval; void *ctx;
     rng_t rng;
+    uint64_t playout_rng;        /* random playouts (NEURAL_NET=False) */
     uint64_t nodes, evals, rollout_count;
 };
 
@@ -471,8 +474,40 @@ static node_t *select_child(cko_tree *t, node_t *nd) {          /* MCTS.py:101-1
     return nd->children[best];
 }
 
+/* NEURAL_NET=False: child.q + 2c * (2 ln(N) / n) ** 0.5, all in float64 -- rewards are Python ints
+ * there, so q is an int / int true division (MCTS.py:113-115, 389-394) */
+static node_t *select_child_uct(cko_tree *t, node_t *nd) {
+    const int b = nd->nchildren;
+    const double ln_n = log((double)nd->n);
+    int best = 0; double best_u = 0;
+    for (int j = 0; j < b; ++j) {
+        const node_t *c = nd->children[j];
+        const double q = c->n ? (double)c->w / (double)c->n : 0.0;
+        const double u = q + (2.0 * t->cfg.uct_c) * pow(2.0 * ln_n / (double)c->n, 0.5);
+        if (j == 0 || u > best_u) { best = j; best_u = u; }
+    }
+    return nd->children[best];
+}
+
+/* MCTS_Node.simulation in that mode: default_policy plays from the node to the end of the game
+ * (a terminal node is its own outcome) and the outcome string is backed up (MCTS.py:132-146, 412-417) */
+static void simulate(cko_tree *t, node_t *nd) {
+    int outcome = nd->status;
+    if (!nd->terminal)
+        outcome = t->cfg.rollout == CKO_ROLLOUT_HASH ? cko_hash_playout(&nd->pos, NULL)
+                                                     : cko_random_playout(&nd->pos, &t->playout_rng, NULL, 0);
+    backprop(t, nd, 1, outcome, 0.f, nd->player);
+}
+
 static void tree_policy(cko_tree *t, node_t *nd) {              /* MCTS.py:59-99 */
     for (;;) {
+        if (nd->n_unvisited && t->cfg.rollout) {                 /* one child per visit (:78-89) */
+            if (!nd->children) nd->children = (node_t **)malloc((size_t)nd->n_unvisited * sizeof(node_t *));
+            node_t *c = node_new(t, &nd->unvisited[--nd->n_unvisited], nd);     /* pop() from the end */
+            nd->children[nd->nchildren++] = c;
+            simulate(t, c);
+            return;
+        }
         if (nd->n_unvisited) {
             float policy[512], prior[512], value;
             t->eval(&nd->pos, nd->mask, nd->plane5, policy, &value, t->ctx);
@@ -493,7 +528,7 @@ static void tree_policy(cko_tree *t, node_t *nd) {              /* MCTS.py:59-99
             fprintf(stderr, "cko: search from a terminal root\n");
             abort();
         }
-        node_t *c = select_child(t, nd);
+        node_t *c = t->cfg.rollout ? select_child_uct(t, nd) : select_child(t, nd);
         if (c->terminal) {                                       /* MCTS.py:93-94,145-146 */
             backprop(t, c, 1, c->status, 0.f, c->player);
             return;
@@ -508,6 +543,7 @@ cko_tree *cko_tree_new(const cko_pos *root, int parent_player, const cko_cfg *cf
     t->eval = eval; t->ctx = ctx;
     t->tau = cfg->tau; t->tau_ref = &t->tau;
     rng_seed(&t->rng, cfg->seed);
+    t->playout_rng = cfg->seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     t->root = node_new(t, root, NULL);
     t->root_parent_player = parent_player >= 0 ? parent_player : 1 - t->root->player;
     return t;
@@ -744,6 +780,30 @@ int cko_random_playout(const cko_pos *pos, uint64_t *rng_state, int *plies, int 
         if (max_plies > 0 && k >= max_plies) break;
         uint64_t r = splitmix64(rng_state);
         cur = ch[(int)(r % (uint64_t)n)];
+        ++k;
+    }
+    if (plies) *plies = k;
+    return st;
+}
+
+/* deterministic stand-in for np.random.randint(0, n) inside a playout: a hash of the position the
+ * move is chosen from (same mixing as the hash evaluator) */
+uint32_t cko_hash_choice(const cko_pos *pos, uint32_t n) {
+    uint32_t h = mix32(pos->p1 ^ 0x9e3779b9u);
+    h = mix32(h ^ pos->p2);
+    h = mix32(h ^ pos->k);
+    h = mix32(h ^ (pos->meta & 1u));
+    return h % n;
+}
+
+int cko_hash_playout(const cko_pos *pos, int *plies) {
+    cko_pos cur = *pos, ch[CKO_MAX_CHILDREN];
+    uint32_t mask[8];
+    int st, p5, n, k = 0;
+    for (;;) {
+        n = cko_movegen(&cur, ch, mask, &st, &p5);
+        if (st != CKO_ONGOING) break;
+        cur = ch[cko_hash_choice(&cur, (uint32_t)n)];
         ++k;
     }
     if (plies) *plies = k;

@@ -64,7 +64,11 @@ typedef struct {
     int32_t tau_decay_delay;          /* TEMP_DECAY_DELAY */
     int32_t terminate_cnt;            /* TERMINATE_CNT, <=0: no cap (tournament) */
     uint64_t seed;
+    int32_t rollout;     /* NEURAL_NET=False: 0 = off (PUCT + evaluator); CKO_ROLLOUT_RANDOM / CKO_ROLLOUT_HASH =
+                          * plain UCT with one playout per simulation (MCTS.py:78-89,113-115,132-143) */
+    int32_t reserved;
 } cko_cfg;
+enum { CKO_ROLLOUT_OFF = 0, CKO_ROLLOUT_RANDOM = 1, CKO_ROLLOUT_HASH = 2 };
 
 typedef struct cko_tree cko_tree;   /* one MCTS tree (MCTS_Node graph + root) */
 typedef struct cko_game cko_game;   /* one self-play / arena game (two trees) */
@@ -117,6 +121,10 @@ uint64_t cko_game_reroot_misses(const cko_game *);
 /* random playout from pos (MCTS.default_policy non-NN branch, MCTS.py:132-143);
  * returns CKO_*; max_plies<=0: unlimited */
 int cko_random_playout(const cko_pos *pos, uint64_t *rng_state, int *plies, int max_plies);
+/* the same playout with np.random.randint replaced by a hash of the current position
+ * (index = cko_hash_choice(position, n_legal)); deterministic twin for parity tests */
+int cko_hash_playout(const cko_pos *pos, int *plies);
+uint32_t cko_hash_choice(const cko_pos *pos, uint32_t n);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ class Cfg(C.Structure):
                 ("alpha", C.c_double), ("epsilon", C.c_double),
                 ("tau", C.c_double), ("tau_decay", C.c_double),
                 ("tau_decay_delay", C.c_int32), ("terminate_cnt", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("rollout", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Record(C.Structure):
@@ -101,6 +101,10 @@ def lib():
         f.restype = C.c_uint64
     L.cko_random_playout.argtypes = [PP, C.POINTER(C.c_uint64), IP, C.c_int]
     L.cko_random_playout.restype = C.c_int
+    L.cko_hash_playout.argtypes = [PP, IP]
+    L.cko_hash_playout.restype = C.c_int
+    L.cko_hash_choice.argtypes = [PP, C.c_uint32]
+    L.cko_hash_choice.restype = C.c_uint32
     _lib = L
     return L
 
@@ -142,9 +146,11 @@ def mask_renorm(policy, mask):
 
 
 def make_cfg(uct_c=4.0, budget=400, training=False, alpha=1.0, epsilon=0.0, tau=0.0,
-             tau_decay=0.0, tau_decay_delay=0, terminate_cnt=0, seed=1):
+             tau_decay=0.0, tau_decay_delay=0, terminate_cnt=0, seed=1, rollout=None):
+    """rollout: None (NEURAL_NET=True), 'random' or 'hash' (NEURAL_NET=False: UCT + one playout per simulation)"""
     return Cfg(float(uct_c), int(budget), int(bool(training)), float(alpha), float(epsilon),
-               float(tau), float(tau_decay), int(tau_decay_delay), int(terminate_cnt), int(seed))
+               float(tau), float(tau_decay), int(tau_decay_delay), int(terminate_cnt), int(seed),
+               {None: 0, "random": 1, "hash": 2}[rollout], 0)
 
 
 BUILTIN_EVALS = ("uniform_zero", "uniform_material", "hash", "hash_salted")
@@ -284,3 +290,14 @@ def random_playout(pos, seed, max_plies=0):
     plies = C.c_int()
     out = lib().cko_random_playout(C.byref(_pos(pos)), C.byref(st), C.byref(plies), max_plies)
     return out, plies.value
+
+
+def hash_playout(pos):
+    """-> (outcome, plies) of the deterministic playout (index = hash_choice(position, n_legal))"""
+    plies = C.c_int()
+    out = lib().cko_hash_playout(C.byref(_pos(pos)), C.byref(plies))
+    return out, plies.value
+
+
+def hash_choice(pos, n):
+    return int(lib().cko_hash_choice(C.byref(_pos(pos)), int(n)))

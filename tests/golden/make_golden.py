@@ -11,6 +11,10 @@ Outputs (all small, committed):
   mcts_kat.json       KAT-A / KAT-B / hash-stub first searches + per-move root statistics
   selfplay_*.npz      full records of _generate_data run verbatim with stub nets
   tournament.json     _start_tournament run verbatim with two different stub nets
+  uct_kat.json        NEURAL_NET=False (UCT + one playout per simulation, the iteration-0 mode): first search
+                      and per-move root statistics of a _generate_data game, with np.random.randint inside
+                      MCTS.default_policy replaced by a hash of the position the move is chosen from
+                      (python tests/golden/make_golden.py uct  regenerates only this file)
 """
 import json
 import os
@@ -186,7 +190,7 @@ def node_children(node):
                  n=int(c.n), w=float(c.w), p=float(c.p), terminal=bool(c.terminal)) for c in node.children]
 
 
-def run_pipeline_game(kind, budget, terminate_cnt, workdir, log):
+def run_pipeline_game(kind, budget, terminate_cnt, workdir, log, **mcts_overrides):
     """generate_Checkers_data._generate_data run verbatim; MCTS.best_child wrapped to log the
     root statistics at every move (the wrapper only observes)."""
     H.set_load_model(lambda path: KerasLikeStub(kind))
@@ -202,7 +206,7 @@ def run_pipeline_game(kind, budget, terminate_cnt, workdir, log):
 
             ref.MCTS.MCTS.best_child = classmethod(spy)
             sp = dict(NUM_SELFPLAY_GAMES=1, TRAINING_ITERATION=0, TERMINATE_CNT=terminate_cnt, NUM_CPUS=1, NN_FN='stub')
-            mk = dict(MCTS_KW, BUDGET=budget, TRAINING=True)
+            mk = dict(MCTS_KW, BUDGET=budget, TRAINING=True, **mcts_overrides)
             fn = ref.training_pipeline.generate_Checkers_data(sp, mk).generate_data()
             data = pickle.load(open(fn, 'rb'))
     finally:
@@ -257,6 +261,50 @@ def make_mcts(workdir):
         print("selfplay", kind, len(data), "records", round(time.time() - t, 1), "s")
 
 
+class hashed_playouts(object):
+    """np.random.randint(0, n) inside MCTS.default_policy (MCTS.py:141) -> oracle.hash_choice(position, n): the
+    reference code runs unmodified, only numpy's generator is replaced, and the replacement looks at the
+    playout environment of the calling frame (``game_sim``) to hash the position the move is chosen from."""
+
+    def __enter__(self):
+        from oracle import oracle as O
+        self.orig = np.random.randint
+
+        def fake_randint(low, high=None, *a, **k):
+            state = sys._getframe(1).f_locals['game_sim'].state
+            bits = [codec.plane_to_bits(state[i]) for i in range(4)]
+            pos = (bits[0] | bits[1], bits[2] | bits[3], bits[1] | bits[3], int(state[4, 0, 0]))
+            return O.hash_choice(pos, high)
+
+        np.random.randint = fake_randint
+        return self
+
+    def __exit__(self, *exc):
+        np.random.randint = self.orig
+
+
+def make_uct(workdir):
+    kat = {}
+    with hashed_playouts():
+        with H.reference_modules() as ref:
+            env = ref.Checkers.Checkers(None)
+            ref.MCTS.MCTS(**dict(MCTS_KW, GAME_ENV=env, NEURAL_NET=False, BUDGET=300))
+            root = ref.MCTS.MCTS_Node(env.state)
+            t = time.time()
+            ref.MCTS.MCTS.begin_tree_search(root)
+            kat["first_search"] = dict(budget=300, root_n=int(root.n), root_w=float(root.w), children=node_children(root))
+            print("uct first search", round(time.time() - t, 1), "s")
+        for name, budget, plies in (("game", 150, 40),):
+            log = []
+            t = time.time()
+            data = run_pipeline_game("uniform_zero", budget, plies, workdir, log, NEURAL_NET=False)
+            kat[name] = dict(budget=budget, terminate_cnt=plies, moves=log,
+                             chosen=[[int(v) for v in e[0][14, 0, 0:3]] for e in data[1:]],
+                             q=[float(e[2]) for e in data], z=[int(e[3]) for e in data])
+            print("uct game", len(log), "plies", round(time.time() - t, 1), "s")
+    json.dump(kat, open(os.path.join(HERE, "uct_kat.json"), "w"))
+
+
 def make_tournament(workdir):
     nets = {"data/model/A": "hash", "data/model/B": "uniform_material"}
     H.set_load_model(lambda path: KerasLikeStub(nets[path]))
@@ -280,11 +328,15 @@ def main():
     os.makedirs(os.path.join(workdir, "data/training_data"))
     os.makedirs(os.path.join(workdir, "data/tournament_results"))
     try:
+        if sys.argv[1:] == ["uct"]:
+            make_uct(workdir)
+            return
         with H.reference_modules() as ref:
             make_movegen(ref)
             make_predict_glue(ref)
             make_perft(ref)
         make_mcts(workdir)
+        make_uct(workdir)
         make_tournament(workdir)
     finally:
         shutil.rmtree(workdir, ignore_errors=True)

@@ -76,6 +76,30 @@ def test_game_opening_golden(kind):
         assert r["visits"] == [c["n"] for c in m["children"]]
 
 
+def test_uct_rollout_mode_golden():
+    """NEURAL_NET=False (MCTS.py:78-89,113-115,132-146): one child per visit, UCT selection, one playout per
+    simulation -- first search and a 40-ply _generate_data game of the reference with hashed playouts."""
+    kat = json.load(open(os.path.join(GOLDEN, "uct_kat.json")))
+    fs = kat["first_search"]
+    t = O.Tree(O.start_position(), O.make_cfg(budget=fs["budget"], rollout="hash"))
+    t.search(fs["budget"])
+    n, w = t.root_stats()
+    assert n == fs["root_n"] and float(w) == fs["root_w"]
+    got = [(codec.meta_action(c["pos"][3]), c["n"], float(c["w"]), bool(c["terminal"])) for c in t.root_children()]
+    assert got == [(c["action"], c["n"], c["w"], c["terminal"]) for c in fs["children"]]
+    gk = kat["game"]
+    g = O.Game(O.make_cfg(budget=gk["budget"], training=True, terminate_cnt=gk["terminate_cnt"], rollout="hash"))
+    g.play()
+    recs = g.records()
+    assert len(recs) == len(gk["moves"]) and g.reroot_misses == 0
+    for r, m, q, z in zip(recs, gk["moves"], gk["q"], gk["z"]):
+        assert r["root_n"] == m["root_n"] and float(r["root_w"]) == m["root_w"]
+        assert r["actions"] == [c["action"] for c in m["children"]]
+        assert r["visits"] == [c["n"] for c in m["children"]]
+        # the record carries q as float32; the reference's int / int quotient is recovered exactly from root_n / root_w
+        assert float(r["q"]) == pytest.approx(q, abs=0, rel=2e-7) and r["z"] == z
+
+
 @pytest.mark.parametrize("kind", ["hash", "uniform_material"])
 def test_selfplay_records_golden(kind):
     f = np.load(os.path.join(GOLDEN, "selfplay_%s.npz" % kind))
