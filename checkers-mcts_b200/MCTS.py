@@ -14,9 +14,9 @@ errors follow the reference:
 Differences that are forced by the device design and stated here rather than hidden:
 ``game_env.neural_net`` must be a device network (``ckb200.net.KerasLikeNet``) or a stub
 (``ckb200.net.StubNet``) -- an arbitrary host ``predict`` object cannot be called from a CUDA
-kernel and there is no CPU fallback; ``CONSTRAINT='time'`` and the net-less random-rollout mode of
-the reference (``NEURAL_NET=False``, MCTS.py:78-89) are served by ``ckb200.lib.rollout`` (K4), not
-by this class.
+kernel and there is no CPU fallback; ``CONSTRAINT='time'`` is not supported.  ``NEURAL_NET=False``
+(MCTS.py:78-89,113-115: plain UCT, one child per visit, one random playout per simulation) runs on
+the device as well and needs no network object.
 """
 from datetime import datetime
 
@@ -70,8 +70,6 @@ class MCTS(object):
         if cls.constraint != 'rollout':
             raise ValueError('Invalid MCTS computational constraint!' if cls.constraint != 'time' else
                              "CONSTRAINT='time' is not supported by the device engine; use 'rollout'")
-        if not cls.neural_net:
-            raise ValueError('NEURAL_NET=False (random rollouts) is served by ckb200.lib.rollout, not by MCTS')
         cls._close_trees()
 
     # ---- engine plumbing ---------------------------------------------------------------------
@@ -82,10 +80,17 @@ class MCTS(object):
         cls._trees = []
 
     @classmethod
+    def _evaluator_kind(cls, net):
+        kind = getattr(net, 'ck_evaluator', None)
+        if not cls.neural_net:       # NEURAL_NET=False: UCT with playouts (MCTS.py:78-89); a StubNet('rollout_hash') picks the deterministic twin
+            return kind if kind in ('rollout', 'rollout_hash') else 'rollout'
+        return kind
+
+    @classmethod
     def _new_tree(cls):
         """a fresh device tree configured from the class-level search parameters"""
         net = getattr(cls.game_env, 'neural_net', None)
-        kind = getattr(net, 'ck_evaluator', None)
+        kind = cls._evaluator_kind(net)
         device = getattr(cls.game_env, 'device', 0)
         if kind is None:
             raise TypeError('game_env.neural_net must be a ckb200 device network (ckb200.net.KerasLikeNet) or a '
@@ -124,11 +129,11 @@ class MCTS(object):
         net = getattr(cls.game_env, 'neural_net', None)
         tree = root_node._tree
         if tree is not None and not tree.closed and tree.kind == "net" and tree.net is not net \
-                and getattr(net, 'ck_evaluator', None) == "net":
+                and cls._evaluator_kind(net) == "net":
             tree.engine.set_net(0, net.net)          # the caller swapped game_env.neural_net (tournaments do)
             tree.net = net
         if tree is None or tree.closed or root_node._idx is None or root_node._epoch != tree.epoch \
-                or tree.kind != getattr(net, 'ck_evaluator', None):
+                or tree.kind != cls._evaluator_kind(net):
             # a node that is not part of a live device tree: start a fresh tree at its state
             tree = cls._new_tree()
             rev, ply = history_counters(root_node.history)
@@ -162,6 +167,8 @@ class MCTS(object):
         """most visited child, or a sample ~ n^(1/tau) while training with tau > 0 (MCTS.py:226-248)"""
         if cls.neural_net:
             criterion = 'robust'
+        if criterion == 'max':                    # highest total reward (NEURAL_NET=False only, MCTS.py:232-234)
+            return node.children[int(np.argmax([child.w for child in node.children]))]
         if criterion != 'robust':
             raise ValueError('Invalid winner selection criterion!')
         children = node.children

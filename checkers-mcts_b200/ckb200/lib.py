@@ -16,8 +16,10 @@ POLICY_SIZE = 512
 NET_PARAM_COUNT = 1321774
 EVAL_NET, EVAL_UNIFORM_ZERO, EVAL_UNIFORM_MATERIAL, EVAL_HASH = 0, 1, 2, 3
 EVAL_HASH_SALTED = 4
+EVAL_ROLLOUT, EVAL_ROLLOUT_HASH = 5, 6      # NEURAL_NET=False: UCT + one playout per simulation
 EVAL_KINDS = {"net": EVAL_NET, "uniform_zero": EVAL_UNIFORM_ZERO, "uniform_material": EVAL_UNIFORM_MATERIAL,
-              "hash": EVAL_HASH, "hash_salted": EVAL_HASH_SALTED}
+              "hash": EVAL_HASH, "hash_salted": EVAL_HASH_SALTED, "rollout": EVAL_ROLLOUT,
+              "rollout_hash": EVAL_ROLLOUT_HASH}
 NET_IMPL_TC, NET_IMPL_SIMT = 0, 1
 
 from .lib_types import GAME_DTYPE, LEAF_DTYPE, POS_DTYPE, RECORD_DTYPE  # noqa: E402,F401

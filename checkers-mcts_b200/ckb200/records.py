@@ -7,8 +7,10 @@ import numpy as np
 from . import codec
 
 
-def to_reference(rec):
-    """one RECORD_DTYPE element -> [state, probs, q, z] exactly as the reference pickles it"""
+def to_reference(rec, playouts=False):
+    """one RECORD_DTYPE element -> [state, probs, q, z] exactly as the reference pickles it.
+    ``playouts``: the record comes from a NEURAL_NET=False search, where rewards are Python ints and
+    ``root.q`` is their float64 quotient (MCTS.py:389-394) -- rebuilt from the exact root_w / root_n."""
     pos = tuple(int(v) for v in rec["pos"])
     state = codec.decode_state(pos, [int(v) for v in rec["mask"]], int(rec["plane5"]))
     n = int(rec["n_children"])
@@ -20,11 +22,15 @@ def to_reference(rec):
         probs /= np.sum(probs)
     probs = probs.reshape(8, 8, 8)
     q = np.float32(rec["q"]) if n else int(rec["q"])      # terminal records carry the Python ints 0 / -1 (:407-408)
+    if n and playouts:
+        q = float(rec["root_w"]) / int(rec["root_n"]) if int(rec["root_n"]) else 0
+        if q * float(rec["q"]) < 0:                       # recorded from the root player's point of view (:365-368)
+            q = -q
     return [state, probs, q, int(rec["z"])]
 
 
-def to_reference_list(records):
-    return [to_reference(r) for r in records]
+def to_reference_list(records, playouts=False):
+    return [to_reference(r, playouts) for r in records]
 
 
 def training_batch(records):

@@ -71,6 +71,9 @@ struct EngineDev {
     ck_record *rec;
     ck_game_result *results;
     const double *pow_half;      // host libm pow(n, 0.5) table (MCTS.py:110 uses n ** 0.5)
+    const double *log_tab;       // host libm log(n) table (np.log(node.n), MCTS.py:114); rollout evaluators only
+    int32_t uct;                 // 1: NEURAL_NET=False tree policy (UCT, one child per visit, playouts)
+    uint32_t round;              // lock-step round counter (keys the random playouts)
 };
 
 // ---- small device helpers --------------------------------------------------------------
@@ -341,6 +344,141 @@ __device__ void expand_pending(const WarpCtx &c) {
     backup(c, S.pend_depth, false, 0, value, lplayer);
 }
 
+// ---- NEURAL_NET=False (the reference's iteration-0 self-play, MCTS.py:78-89,113-115,132-146) ---------
+// Plain UCT: a node with unvisited successors adds ONE child per visit and plays the game out from it;
+// a fully expanded node picks argmax q + 2c * (2 ln N / n) ** 0.5 in float64 (rewards are integers there,
+// so q is an int / int quotient).  The block of all successors is laid out at the node's first visit
+// (creating a node has no side effect in the reference beyond its own move generation) and the node's
+// otherwise unused prior field counts how many of them exist for the search: children [0, count).
+__device__ __forceinline__ int uct_expanded(const uint4 st) { return min((int)st.z, link_nchild(st.w)); }
+
+__device__ int select_leaf_uct(const WarpCtx &c, int *out_depth) {
+    const EngineDev &E = c.E;
+    Slot &S = c.S;
+    const int t = S.cur;
+    uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
+    int node = S.root[t], depth = 0;
+    if (c.lane == 0) c.path[0] = (uint32_t)node;
+    for (;;) {
+        const uint4 st = stat[node];
+        int b = link_nchild(st.w), fc = (int)(st.w & kFcMask), k = (int)st.z;
+        if (b == 0) {                                    // first visit: lay out the successor block
+            const ck_pos lp = to_pos(pos[node]);
+            uint32_t mask[8];
+            b = gen_moves(lp, NullSink{}, mask);
+            const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+            const uint32_t use[4] = {jump ? mask[4] : mask[0], jump ? mask[5] : mask[1], jump ? mask[6] : mask[2], jump ? mask[7] : mask[3]};
+            const Side lsd = side_of(lp);
+            uint32_t hop[4];
+            hop_sets(lsd, hop);
+            fc = S.alloc[t];
+            if (b == 0 || fc + b > E.cap) {
+                dev_error(E, b == 0 ? CK_ERR_STATE : CK_ERR_POOL_OVERFLOW);
+                *out_depth = depth;
+                return -2;
+            }
+            const int lplayer = meta_player(lp.meta);
+            for (int i = c.lane; i < b; i += 32) {
+                int ms, md;
+                kth_move(lsd, use, jump, b - 1 - i, &ms, &md);             // unvisited_child_states.pop(): last first
+                const ck_pos ch = make_child_fast(lp, lsd, hop, ms, md, jump);
+                int p5;
+                const int stc = status_of(ch, &p5);
+                pos[fc + i] = from_pos(ch);
+                stat[fc + i] = make_uint4(0u, __float_as_uint(0.f), 0u, ((uint32_t)stc << 28) | ((uint32_t)lplayer << 30));
+            }
+            __syncwarp();
+            if (c.lane == 0) {
+                stat[node].w = (st.w & 0xF0000000u) | ((uint32_t)b << 22) | (uint32_t)fc;
+                S.alloc[t] = fc + b;
+            }
+            k = 0;
+        }
+        if (k < b) {                                     // add the next child and simulate from it (:78-89)
+            const int child = fc + k;
+            ++depth;
+            if (depth >= kMaxDepth) { dev_error(E, CK_ERR_DEPTH); *out_depth = depth - 1; return -2; }
+            if (c.lane == 0) {
+                stat[node].z = (uint32_t)(k + 1);
+                c.path[depth] = (uint32_t)child;
+                atomicAdd(&E.ctr->nodes, 1ull);
+            }
+            __syncwarp();
+            const int cs = link_status(stat[child].w);
+            if (cs != CK_ONGOING) { backup(c, depth, true, cs, 0.f, 0); return -1; }   // a terminal node is its own outcome
+            *out_depth = depth;
+            return child;
+        }
+        const uint32_t pn = st.x;
+        const double ln_n = pn < (uint32_t)kPowTable ? E.log_tab[pn] : log((double)pn);
+        const double two_ln = __dmul_rn(2.0, ln_n), two_c = __dmul_rn(2.0, E.cfg.uct_c);
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        if (c.lane < b) c0 = stat[fc + c.lane];
+        if (c.lane + 32 < b) c1 = stat[fc + 32 + c.lane];
+        double best_u = 0.0;
+        int best_i = kNoIdx;
+        if (c.lane < b) {
+            const double q = c0.x ? __ddiv_rn((double)__uint_as_float(c0.y), (double)c0.x) : 0.0;
+            best_u = __dadd_rn(q, __dmul_rn(two_c, sqrt(__ddiv_rn(two_ln, (double)c0.x))));
+            best_i = c.lane;
+        }
+        if (c.lane + 32 < b) {
+            const double q = c1.x ? __ddiv_rn((double)__uint_as_float(c1.y), (double)c1.x) : 0.0;
+            const double u1 = __dadd_rn(q, __dmul_rn(two_c, sqrt(__ddiv_rn(two_ln, (double)c1.x))));
+            if (u1 > best_u) { best_u = u1; best_i = c.lane + 32; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ou = shfl_xor_d(best_u, o);
+            const int oi = __shfl_xor_sync(CK_FULL, best_i, o);
+            const bool take = (oi != kNoIdx) && (best_i == kNoIdx || ou > best_u || (ou == best_u && oi < best_i));
+            if (take) { best_u = ou; best_i = oi; }
+        }
+        const uint32_t plink = best_i < 32 ? __shfl_sync(CK_FULL, c0.w, best_i) : __shfl_sync(CK_FULL, c1.w, best_i - 32);
+        node = fc + best_i;
+        ++depth;
+        if (depth >= kMaxDepth) { dev_error(E, CK_ERR_DEPTH); *out_depth = depth - 1; return -2; }
+        if (c.lane == 0) c.path[depth] = (uint32_t)node;
+        const int cs = link_status(plink);
+        if (cs != CK_ONGOING) {
+            __syncwarp();
+            backup(c, depth, true, cs, 0.f, 0);
+            return -1;
+        }
+    }
+}
+
+// stage the start of a playout: position with its draw-rule counters (meta rides in mask[0])
+__device__ void stage_playout(const WarpCtx &c, int leaf, int depth) {
+    const EngineDev &E = c.E;
+    Slot &S = c.S;
+    __syncwarp();
+    if (c.lane == 0) {
+        const ck_pos p = to_pos(c.pos_of(S.cur)[leaf]);
+        ck_leaf L;
+        L.p1 = p.p1; L.p2 = p.p2; L.k = p.k;
+        L.info = (p.meta & 1u) | (((uint32_t)global_game(E, S.game) & 0xFFFFu) << 16);
+        L.mask[0] = p.meta;
+#pragma unroll
+        for (int i = 1; i < 8; ++i) L.mask[i] = 0u;
+        const int row = atomicAdd(&E.ctr->batch_count[0], 1);
+        E.leaves[0][row] = L;
+        S.pend_leaf = leaf; S.pend_row = row; S.pend_depth = depth; S.pend_net = 0;
+    }
+    __syncwarp();
+}
+
+// the playout's outcome string is backed up from the node it started at (MCTS_Node.simulation, :412-417)
+__device__ void finish_playout(const WarpCtx &c) {
+    Slot &S = c.S;
+    const int outcome = (int)c.E.value[0][S.pend_row];
+    const int depth = S.pend_depth;
+    __syncwarp();
+    if (c.lane == 0) { S.pend_leaf = -1; S.tot_evals += 1; S.tot_sims += 1; S.sims_done += 1; }
+    __syncwarp();
+    backup(c, depth, true, outcome, 0.f, 0);
+}
+
 // K5: copy the subtree under `root` of tree t into the scratch buffer in BFS order and make
 // the scratch buffer the tree's buffer.  32 nodes per iteration: each lane relocates the
 // child block of one node; block positions come from a warp prefix sum.
@@ -423,8 +561,9 @@ __device__ void setup_root(const WarpCtx &c) {
         int nr = S.best[t];
         for (int i = L - counter; i < L; ++i) {
             const ck_pos want = c.hist[i];
-            const uint32_t link = stat[nr].w;
-            const int b = link_nchild(link), fc = (int)(link & kFcMask);
+            const uint4 nst = stat[nr];
+            const uint32_t link = nst.w;
+            const int b = E.uct ? uct_expanded(nst) : link_nchild(link), fc = (int)(link & kFcMask);
             int found = kNoIdx;
             for (int j = c.lane; j < b; j += 32)
                 if (found == kNoIdx && same_state(to_pos(pos[fc + j]), want)) found = j;
@@ -505,7 +644,7 @@ __device__ bool play_move(const WarpCtx &c) {
     const int root = S.root[t];
     const uint4 rst = stat[root];
     const ck_pos rpos = to_pos(pos[root]);
-    const int b = link_nchild(rst.w), fc = (int)(rst.w & kFcMask);
+    const int b = E.uct ? uct_expanded(rst) : link_nchild(rst.w), fc = (int)(rst.w & kFcMask);
     const int parent_player = link_pp(rst.w);
     uint32_t n0 = 0, n1 = 0;
     ck_pos k0 = rpos, k1 = rpos;
@@ -633,6 +772,7 @@ __device__ bool play_move(const WarpCtx &c) {
 #ifndef CK_TREE_OCC
 #define CK_TREE_OCC 5
 #endif
+template <bool kUct>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, CK_TREE_OCC)
 tree_step_kernel(const EngineDev E) {
     __shared__ Slot s_slot[kWarpsPerBlock];
@@ -651,7 +791,7 @@ tree_step_kernel(const EngineDev E) {
     if (E.ctr->error != 0) live = false;
     if (live && S.game < 0) live = S.manual ? false : refill(c);
     if (live && S.phase == PH_HALT) live = false;
-    if (live && S.pend_leaf >= 0) expand_pending(c);
+    if (live && S.pend_leaf >= 0) { if (kUct) finish_playout(c); else expand_pending(c); }
     int term_iters = 0;
     const int max_term = E.max_term;
     while (live && S.phase != PH_HALT) {
@@ -663,8 +803,8 @@ tree_step_kernel(const EngineDev E) {
             continue;
         }
         int depth = 0;
-        const int leaf = select_leaf(c, &depth);
-        if (leaf >= 0) { stage_leaf(c, leaf, depth); break; }
+        const int leaf = kUct ? select_leaf_uct(c, &depth) : select_leaf(c, &depth);
+        if (leaf >= 0) { if (kUct) stage_playout(c, leaf, depth); else stage_leaf(c, leaf, depth); break; }
         __syncwarp();
         if (leaf == -2) { if (lane == 0) S.phase = PH_HALT; __syncwarp(); break; }
         if (lane == 0) { S.tot_sims += 1; S.sims_done += 1; }
@@ -750,6 +890,44 @@ stub_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restrict__
     }
 }
 
+// Playouts of the staged positions (MCTS.default_policy without a net, MCTS.py:132-143): thread per game,
+// uniformly random legal successors until determine_outcome ends the game; value[row] = CK_* outcome.
+// CK_EVAL_ROLLOUT_HASH replaces the random index by a hash of the position the move is chosen from
+// (twin of the oracle's cko_hash_choice) so that whole searches can be compared bit for bit.
+__global__ void __launch_bounds__(128)
+playout_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restrict__ n_dev, int kind, uint64_t seed,
+                    uint32_t round, float *__restrict__ value) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= *n_dev) return;
+    const ck_leaf L = leaves[row];
+    ck_pos cur;
+    cur.p1 = L.p1; cur.p2 = L.p2; cur.k = L.k; cur.meta = L.mask[0];
+    const Philox rng(mix64(seed ^ mix64(((uint64_t)(L.info >> 16) << 32) | round)));
+    uint32_t r[4];
+    int st;
+    for (int k = 0;; ++k) {
+        uint32_t mask[8];
+        const int cnt = gen_moves(cur, NullSink{}, mask);
+        st = outcome_of(cur, cnt > 0, nullptr);
+        if (st != CK_ONGOING) break;
+        int pick;
+        if (kind == CK_EVAL_ROLLOUT_HASH) {
+            uint32_t h = mix32(cur.p1 ^ 0x9e3779b9u ^ ((L.info >> 16) * 0x9E3779B1u));      // salted with the game tag
+            h = mix32(h ^ cur.p2);
+            h = mix32(h ^ cur.k);
+            h = mix32(h ^ (cur.meta & 1u));
+            pick = (int)(h % (uint32_t)cnt);
+        } else {
+            if ((k & 3) == 0) rng((uint32_t)(k >> 2), 0u, 0u, 0x504C4159u, r);
+            pick = (int)(((uint64_t)r[k & 3] * (uint64_t)cnt) >> 32);
+        }
+        ck_pos nxt = cur;
+        gen_moves(cur, PickSink{&nxt, pick}, mask);
+        cur = nxt;
+    }
+    value[row] = (float)st;
+}
+
 }  // namespace ck
 
 // =================================================================================================
@@ -780,7 +958,7 @@ static void engine_free(ck_engine *e) {
     EngineDev &d = e->dev;
     cudaFree(d.pos); cudaFree(d.stat); cudaFree(d.hist); cudaFree(d.path); cudaFree(d.slots); cudaFree(d.ctr);
     for (int k = 0; k < 2; ++k) { cudaFree(d.leaves[k]); cudaFree(d.policy[k]); cudaFree(d.value[k]); }
-    cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half); cudaFree(e->d_tot);
+    cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half); cudaFree((void *)d.log_tab); cudaFree(e->d_tot);
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->stream_b) cudaStreamDestroy(e->stream_b);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -806,6 +984,12 @@ extern "C" {
 
 ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     if (!cfg || cfg->n_slots < 1 || cfg->budget < 1) { fail(CK_ERR_ARG, "ck_engine_create: n_slots and budget must be >= 1"); return nullptr; }
+    const bool uct = cfg->evaluator == CK_EVAL_ROLLOUT || cfg->evaluator == CK_EVAL_ROLLOUT_HASH;
+    if (cfg->evaluator < CK_EVAL_NET || cfg->evaluator > CK_EVAL_ROLLOUT_HASH) { fail(CK_ERR_ARG, "ck_engine_create: unknown evaluator"); return nullptr; }
+    if (cfg->arena && (uct || cfg->evaluator_p2 == CK_EVAL_ROLLOUT || cfg->evaluator_p2 == CK_EVAL_ROLLOUT_HASH)) {
+        fail(CK_ERR_ARG, "ck_engine_create: the playout evaluators (NEURAL_NET=False) are a self-play mode, not an arena evaluator");
+        return nullptr;
+    }
     DeviceGuard g(cfg->device);
     if (!g.ok) { fail(CK_ERR_CUDA, "ck_engine_create: cannot select CUDA device " + std::to_string(cfg->device)); return nullptr; }
     ck_engine *e = new ck_engine();
@@ -868,6 +1052,17 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         double *p = nullptr;
         CK_E(cudaMalloc(&p, kPowTable * sizeof(double)));
         d.pow_half = p;
+        CK_E(cudaMemcpy(p, tab.data(), kPowTable * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    d.uct = uct ? 1 : 0;
+    if (uct) {
+        // np.log(node.n) for every parent visit count a search can reach, from the host's libm like pow_half
+        std::vector<double> tab(kPowTable);
+        tab[0] = 0.0;
+        for (int i = 1; i < kPowTable; ++i) tab[i] = log((double)i);
+        double *p = nullptr;
+        CK_E(cudaMalloc(&p, kPowTable * sizeof(double)));
+        d.log_tab = p;
         CK_E(cudaMemcpy(p, tab.data(), kPowTable * sizeof(double), cudaMemcpyHostToDevice));
     }
     {
@@ -942,6 +1137,14 @@ int ck_engine_begin(ck_engine *e, int64_t n_games) {
     return CK_OK;
 }
 
+static void launch_tree_step(ck_engine *e) {
+    EngineDev &d = e->dev;
+    const int grid = (d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    d.round += 1;
+    if (d.uct) tree_step_kernel<true><<<grid, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+    else tree_step_kernel<false><<<grid, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+}
+
 static int engine_eval(ck_engine *e, int *launches) {
     EngineDev &d = e->dev;
     // arena: the two networks' batches are independent (each at most half of the slots), so the second one
@@ -955,7 +1158,11 @@ static int engine_eval(ck_engine *e, int *launches) {
         cudaStream_t st = (fork && k == 1) ? e->stream_b : e->stream;
         int kind = d.cfg.evaluator;
         if (k == 1 && d.cfg.evaluator_p2 >= 0) kind = d.cfg.evaluator_p2;
-        if (kind == CK_EVAL_NET) {
+        if (kind == CK_EVAL_ROLLOUT || kind == CK_EVAL_ROLLOUT_HASH) {
+            playout_eval_kernel<<<(d.n_slots + 127) / 128, 128, 0, st>>>(d.leaves[k], &d.ctr->batch_count[k], kind, d.cfg.seed,
+                                                                        d.round, d.value[k]);
+            if (launches) *launches += 1;
+        } else if (kind == CK_EVAL_NET) {
             int rc = net_forward_rows(e->net[k], d.leaves[k], d.n_slots, &d.ctr->batch_count[k], d.policy[k], d.value[k], st, launches);
             if (rc != CK_OK) return rc;
         } else {
@@ -974,7 +1181,7 @@ static int engine_eval(ck_engine *e, int *launches) {
 static int engine_round(ck_engine *e, int *launches) {
     EngineDev &d = e->dev;
     CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));   // active + batch_count[2]
-    tree_step_kernel<<<(d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+    launch_tree_step(e);
     if (launches) *launches += 1;
     CK_CUDA(cudaGetLastError());
     return engine_eval(e, launches);
@@ -1014,7 +1221,7 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         for (int64_t i = 0; i < chunk; ++i) {
             if (e->profile) {
                 CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));
-                tree_step_kernel<<<(d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+                launch_tree_step(e);
                 ++launches;
                 CK_CUDA(cudaEventRecord(e->prof_ev[3 * i], e->stream));
                 if (e->net[0]) e->net[0]->ev_after_tower = e->prof_ev[3 * i + 1];
@@ -1229,7 +1436,7 @@ int ck_tree_root(ck_engine *e, uint32_t *n, float *w, int32_t *n_children) {
     CK_CUDA(cudaMemcpy(&st, d.stat + (size_t)s.buf[s.cur] * d.cap + s.root[s.cur], sizeof(st), cudaMemcpyDeviceToHost));
     if (n) *n = st.x;
     if (w) memcpy(w, &st.y, 4);
-    if (n_children) *n_children = (int32_t)((st.w >> 22) & 63u);
+    if (n_children) *n_children = d.uct ? std::min<int32_t>((int32_t)st.z, (int32_t)((st.w >> 22) & 63u)) : (int32_t)((st.w >> 22) & 63u);
     return CK_OK;
 }
 
@@ -1247,7 +1454,9 @@ int ck_tree_children(ck_engine *e, int32_t node, int32_t *idx, ck_pos *pos, uint
     if (node >= s.alloc[s.cur]) return fail(CK_ERR_ARG, "ck_tree_children: node id out of range");
     uint4 st;
     CK_CUDA(cudaMemcpy(&st, d.stat + base + node, sizeof(st), cudaMemcpyDeviceToHost));
-    const int b = (int)((st.w >> 22) & 63u), fc = (int)(st.w & kFcMask);
+    int b = (int)((st.w >> 22) & 63u);
+    const int fc = (int)(st.w & kFcMask);
+    if (d.uct) b = std::min(b, (int)st.z);                // NEURAL_NET=False: only the children added so far exist
     *count = b;
     if (b == 0) return CK_OK;
     uint4 cs[CK_MAX_CHILDREN], cp[CK_MAX_CHILDREN];

@@ -162,8 +162,6 @@ def _engine_cfg(mcts_kwargs, n_slots, terminate_cnt, evaluator, evaluator_p2=Non
                 device=0, seed=None, game_id_base=0, game_id_stride=1):
     if mcts_kwargs.get('CONSTRAINT', 'rollout') != 'rollout':
         raise ValueError("the device engine only supports CONSTRAINT='rollout'")
-    if not mcts_kwargs.get('NEURAL_NET', True):
-        raise ValueError("NEURAL_NET=False (random rollouts) is served by ckb200.lib.rollout")
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")          # np.random.seed() from OS entropy (:341)
     return _L.make_cfg(n_slots=n_slots, budget=mcts_kwargs['BUDGET'], device=device, uct_c=mcts_kwargs['UCT_C'],
@@ -201,7 +199,10 @@ class generate_Checkers_data(object):
     def generate_data(self):
         """plays NUM_SELFPLAY_GAMES x NUM_CPUS games on the GPU; returns the list of pickle files,
         one per worker as in the reference (a single name when NUM_CPUS == 1)"""
-        spec = load_blob(self.nn_fn)
+        # NEURAL_NET=False is the reference's iteration-0 mode (train_Checkers.py:78): plain UCT with random
+        # playouts, no network involved (the reference still loads NN_FN there and never calls it)
+        playouts = not self.mcts_kwargs.get('NEURAL_NET', True)
+        spec = self.mcts_kwargs.get('PLAYOUT_EVALUATOR', 'rollout') if playouts else load_blob(self.nn_fn)
         total = self.NUM_SELFPLAY_GAMES * self.num_cpus
         cfg = _engine_cfg(self.mcts_kwargs, min(total, self.max_slots), self.TERMINATE_CNT,
                           spec if isinstance(spec, str) else "net", device=self.device, seed=self.seed)
@@ -219,7 +220,7 @@ class generate_Checkers_data(object):
         filenames = []
         for proc in range(self.num_cpus):                 # worker p played games [p*N, (p+1)*N)
             lo, hi = proc * self.NUM_SELFPLAY_GAMES, (proc + 1) * self.NUM_SELFPLAY_GAMES
-            memory = _R.to_reference_list(recs[(recs["game"] >= lo) & (recs["game"] < hi)])
+            memory = _R.to_reference_list(recs[(recs["game"] >= lo) & (recs["game"] < hi)], playouts)
             filenames.append(self._save_memory(memory, self.TRAINING_ITERATION, timestamp, proc))
         return filenames if self.num_cpus > 1 else filenames[0]
 

@@ -114,7 +114,11 @@ int ck_mask_renorm(int device, const float *policy, const uint32_t *masks, int64
  * generate_Checkers_data._generate_data (training_pipeline.py:334-419) and
  * tournament_Checkers._start_tournament (:505-559). */
 enum { CK_EVAL_NET = 0, CK_EVAL_UNIFORM_ZERO = 1, CK_EVAL_UNIFORM_MATERIAL = 2, CK_EVAL_HASH = 3,
-       CK_EVAL_HASH_SALTED = 4 /* hash stub salted with the global game id: concurrent games differ */ };
+       CK_EVAL_HASH_SALTED = 4 /* hash stub salted with the global game id: concurrent games differ */,
+       /* NEURAL_NET=False (MCTS.py:78-89,113-115,132-146): plain UCT, one child added per visit, one playout to the
+        * end of the game per simulation -- the reference's iteration-0 self-play.  Self-play engines only. */
+       CK_EVAL_ROLLOUT = 5      /* uniformly random playouts */,
+       CK_EVAL_ROLLOUT_HASH = 6 /* playout moves picked by a hash of the position (deterministic parity tests) */ };
 
 typedef struct {
     int32_t device;

@@ -494,7 +494,7 @@ static node_t *select_child_uct(cko_tree *t, node_t *nd) {
 static void simulate(cko_tree *t, node_t *nd) {
     int outcome = nd->status;
     if (!nd->terminal)
-        outcome = t->cfg.rollout == CKO_ROLLOUT_HASH ? cko_hash_playout(&nd->pos, NULL)
+        outcome = t->cfg.rollout == CKO_ROLLOUT_HASH ? cko_hash_playout(&nd->pos, t->ctx ? *(const uint32_t *)t->ctx : 0u, NULL)
                                                      : cko_random_playout(&nd->pos, &t->playout_rng, NULL, 0);
     backprop(t, nd, 1, outcome, 0.f, nd->player);
 }
@@ -787,23 +787,24 @@ int cko_random_playout(const cko_pos *pos, uint64_t *rng_state, int *plies, int 
 }
 
 /* deterministic stand-in for np.random.randint(0, n) inside a playout: a hash of the position the
- * move is chosen from (same mixing as the hash evaluator) */
-uint32_t cko_hash_choice(const cko_pos *pos, uint32_t n) {
-    uint32_t h = mix32(pos->p1 ^ 0x9e3779b9u);
+ * move is chosen from (same mixing as the hash evaluator); salt = game tag, 0 for the golden vectors */
+static uint32_t hash_choice(const cko_pos *pos, uint32_t n, uint32_t salt) {
+    uint32_t h = mix32(pos->p1 ^ 0x9e3779b9u ^ (salt * 0x9E3779B1u));
     h = mix32(h ^ pos->p2);
     h = mix32(h ^ pos->k);
     h = mix32(h ^ (pos->meta & 1u));
     return h % n;
 }
+uint32_t cko_hash_choice(const cko_pos *pos, uint32_t n) { return hash_choice(pos, n, 0u); }
 
-int cko_hash_playout(const cko_pos *pos, int *plies) {
+int cko_hash_playout(const cko_pos *pos, uint32_t salt, int *plies) {
     cko_pos cur = *pos, ch[CKO_MAX_CHILDREN];
     uint32_t mask[8];
     int st, p5, n, k = 0;
     for (;;) {
         n = cko_movegen(&cur, ch, mask, &st, &p5);
         if (st != CKO_ONGOING) break;
-        cur = ch[cko_hash_choice(&cur, (uint32_t)n)];
+        cur = ch[hash_choice(&cur, (uint32_t)n, salt)];
         ++k;
     }
     if (plies) *plies = k;

@@ -122,8 +122,9 @@ uint64_t cko_game_reroot_misses(const cko_game *);
  * returns CKO_*; max_plies<=0: unlimited */
 int cko_random_playout(const cko_pos *pos, uint64_t *rng_state, int *plies, int max_plies);
 /* the same playout with np.random.randint replaced by a hash of the current position
- * (index = cko_hash_choice(position, n_legal)); deterministic twin for parity tests */
-int cko_hash_playout(const cko_pos *pos, int *plies);
+ * (index = cko_hash_choice(position, n_legal), optionally salted with a game tag -- the evaluator ctx of
+ * cko_game_new / cko_tree_new); deterministic twin for parity tests */
+int cko_hash_playout(const cko_pos *pos, uint32_t salt, int *plies);
 uint32_t cko_hash_choice(const cko_pos *pos, uint32_t n);
 
 #ifdef __cplusplus

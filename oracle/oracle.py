@@ -101,7 +101,7 @@ def lib():
         f.restype = C.c_uint64
     L.cko_random_playout.argtypes = [PP, C.POINTER(C.c_uint64), IP, C.c_int]
     L.cko_random_playout.restype = C.c_int
-    L.cko_hash_playout.argtypes = [PP, IP]
+    L.cko_hash_playout.argtypes = [PP, C.c_uint32, IP]
     L.cko_hash_playout.restype = C.c_int
     L.cko_hash_choice.argtypes = [PP, C.c_uint32]
     L.cko_hash_choice.restype = C.c_uint32
@@ -292,10 +292,10 @@ def random_playout(pos, seed, max_plies=0):
     return out, plies.value
 
 
-def hash_playout(pos):
+def hash_playout(pos, salt=0):
     """-> (outcome, plies) of the deterministic playout (index = hash_choice(position, n_legal))"""
     plies = C.c_int()
-    out = lib().cko_hash_playout(C.byref(_pos(pos)), C.byref(plies))
+    out = lib().cko_hash_playout(C.byref(_pos(pos)), int(salt), C.byref(plies))
     return out, plies.value
 
 

@@ -299,6 +299,115 @@ def test_concurrent_games_vs_oracle(lib, slots, compact):
     eng.close()
 
 
+def test_uct_first_search_golden_and_midgame_vs_oracle(lib):
+    """NEURAL_NET=False tree policy (MCTS.py:78-89,113-115): one child per visit, UCT in float64, one playout
+    per simulation.  With hashed playouts the whole search is deterministic: the reference's own first search
+    (uct_kat.json) and an oracle search from a mid-game position with tree reuse."""
+    fs = json.load(open(os.path.join(GOLDEN, "uct_kat.json")))["first_search"]
+    eng = lib.Engine(lib.make_cfg(n_slots=1, budget=fs["budget"], evaluator="rollout_hash", keep_records=False))
+    eng.tree_set_root(O.start_position())
+    eng.tree_search(fs["budget"])
+    n, w, b = eng.tree_root()
+    assert n == fs["root_n"] and float(w) == fs["root_w"] and b == len(fs["children"])
+    got = [(codec.meta_action(c["pos"][3]), c["n"], float(c["w"]), bool(c["terminal"])) for c in eng.tree_root_children()]
+    assert got == [(c["action"], c["n"], c["w"], c["terminal"]) for c in fs["children"]]
+    # partially expanded root (budget below the number of moves), then reuse after advancing
+    pos = O.start_position()
+    rng = np.random.RandomState(5)
+    for _ in range(23):
+        kids = O.movegen(pos)[0]
+        pos = kids[rng.randint(len(kids))]
+    t = O.Tree(pos, O.make_cfg(budget=3, rollout="hash"))
+    eng.tree_set_root(pos)
+    for sims in (3, 90, 200):
+        t.search(sims)
+        eng.tree_search(sims)
+        ref = t.root_children()
+        assert eng.tree_root()[:2] == t.root_stats() and eng.tree_root()[2] == len(ref)
+        assert [(c["pos"], c["n"], float(c["w"])) for c in eng.tree_root_children()] == \
+               [(c["pos"], c["n"], float(c["w"])) for c in ref]
+    eng.close()
+
+
+def test_uct_selfplay_game_golden(lib):
+    """_generate_data with NEURAL_NET=False run verbatim (hashed playouts): every search of a 40-ply game"""
+    gk = json.load(open(os.path.join(GOLDEN, "uct_kat.json")))["game"]
+    eng = lib.Engine(lib.make_cfg(n_slots=1, budget=gk["budget"], training=True, terminate_cnt=gk["terminate_cnt"],
+                                  evaluator="rollout_hash"))
+    st = eng.selfplay(1)
+    recs, games = _engine_records(lib, eng)
+    recs = recs[0]
+    assert len(recs) == len(gk["moves"]) and games[0]["reroot_misses"] == 0
+    assert st["sims"] == gk["budget"] * len(recs)
+    for r, m, q, z in zip(recs, gk["moves"], gk["q"], gk["z"]):
+        assert r["root_n"] == m["root_n"] and float(r["root_w"]) == m["root_w"]
+        assert r["actions"] == [c["action"] for c in m["children"]]
+        assert r["visits"] == [c["n"] for c in m["children"]]
+        assert r["z"] == z
+    from ckb200 import records as R
+    for ref_rec, q in zip(R.to_reference_list(eng.records(), playouts=True), gk["q"]):
+        assert type(ref_rec[2]) is type(q) or q == 0
+        assert ref_rec[2] == q                                  # float64 int / int quotient, exact
+    eng.close()
+
+
+@pytest.mark.parametrize("slots,compact", [(16, False), (5, True)])
+def test_uct_concurrent_games_vs_oracle(lib, slots, compact):
+    """many playout-mode games in flight (hashed playouts salted per game so that the games differ), slots
+    refilled, low budget so that roots are only partially expanded and replies go missing from the re-used
+    tree: every record, the miss counts and the simulation totals equal the oracle's"""
+    n_games, budget, term = 24, 20, 60
+    ref = []
+    for g in range(n_games):
+        gm = O.Game(O.make_cfg(budget=budget, training=True, terminate_cnt=term, rollout="hash"), salt=g)
+        gm.play()
+        ref.append((gm.records(), gm.outcome, gm.move_count, gm.terminated, gm.total_sims, gm.reroot_misses))
+        gm.close()
+    eng = lib.Engine(lib.make_cfg(n_slots=slots, budget=budget, training=True, terminate_cnt=term,
+                                  evaluator="rollout_hash", compact_always=compact, pool_cap=8192 if compact else 0))
+    st = eng.selfplay(n_games)
+    recs, games = _engine_records(lib, eng)
+    assert len(games) == n_games
+    for g in range(n_games):
+        rr, outcome, move_count, terminated, sims, misses = ref[g]
+        assert int(games[g]["outcome"]) == outcome and int(games[g]["move_count"]) == move_count
+        assert bool(games[g]["terminated"]) == terminated and int(games[g]["reroot_misses"]) == misses
+        assert int(games[g]["sims"]) == sims
+        assert len(recs[g]) == len(rr)
+        for a, b in zip(recs[g], rr):
+            assert _same_record(a, b)
+    assert sum(r[5] for r in ref) > 0                           # the fresh-root path was exercised
+    assert st["games_finished"] == n_games
+    eng.close()
+
+
+def test_uct_random_playouts_properties(lib):
+    """CK_EVAL_ROLLOUT (Philox playouts, no bit parity with numpy): exact simulation accounting, reproducible per
+    seed, different across seeds, integer rewards"""
+    def run(seed):
+        eng = lib.Engine(lib.make_cfg(n_slots=32, budget=60, training=True, tau=1.0, tau_decay=0.1, tau_decay_delay=10,
+                                      terminate_cnt=50, evaluator="rollout", seed=seed))
+        st = eng.selfplay(48)
+        recs, games = _engine_records(lib, eng)
+        eng.close()
+        return st, recs, games
+    st, recs, games = run(7)
+    assert st["games_finished"] == 48 and len(games) == 48
+    for g, rr in recs.items():
+        searches = [r for r in rr if r["actions"]]
+        assert int(games[g]["sims"]) == 60 * len(searches)
+        for r in searches:
+            assert float(r["root_w"]) == int(r["root_w"]) and abs(float(r["root_w"])) <= r["root_n"]
+            assert sum(r["visits"]) <= r["root_n"] and all(v >= 1 for v in r["visits"])
+            assert r["chosen"] in r["actions"]
+    st2, recs2, _ = run(7)
+    assert all(_same_record(a, b) for g in recs for a, b in zip(recs[g], recs2[g]))
+    _, recs3, _ = run(8)
+    assert any(not _same_record(a, b) for g in recs for a, b in zip(recs[g], recs3[g]))
+    with pytest.raises(lib.CkError):
+        lib.Engine(lib.make_cfg(n_slots=2, budget=10, arena=True, evaluator="rollout"))
+
+
 def test_long_game_draw_rule_vs_oracle(lib):
     """no ply cap: games run into the 80-ply draw window / long endgames (arena semantics)."""
     ref = _oracle_games(6, 24, 0, training=False)

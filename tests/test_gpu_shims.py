@@ -128,6 +128,38 @@ def test_play_loop_two_trees_matches_reference_game(mods, engine_options):
     assert len(mods[1].MCTS._trees) == 2                       # one device tree per player
 
 
+def test_iteration0_selfplay_without_network(mods, tmp_path, monkeypatch):
+    """train_Checkers.py iteration 0: NEURAL_NET=False self-play through generate_Checkers_data and the MCTS
+    shim -- same records as the reference's own _generate_data game (uct_kat.json, hashed playouts)"""
+    C, M, T = mods
+    import play_Checkers as P
+    from ckb200.net import StubNet
+    gk = json.load(open(os.path.join(GOLDEN, "uct_kat.json")))["game"]
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/training_data")
+    sp = dict(NUM_SELFPLAY_GAMES=1, TRAINING_ITERATION=0, TERMINATE_CNT=gk["terminate_cnt"], NUM_CPUS=1, NN_FN=None, SEED=3)
+    mk = dict(MCTS_KW, BUDGET=gk["budget"], TRAINING=True, NEURAL_NET=False, PLAYOUT_EVALUATOR='rollout_hash')
+    data = pickle.load(open(T.generate_Checkers_data(sp, mk).generate_data(), 'rb'))
+    assert len(data) == len(gk["q"])
+    for e, m, q, z in zip(data, gk["moves"], gk["q"], gk["z"]):
+        assert e[2] == q and e[3] == z and e[0].shape == (15, 8, 8) and e[1].shape == (8, 8, 8)
+        total = sum(c["n"] for c in m["children"])
+        for c in m["children"]:
+            assert e[1].reshape(512)[c["action"]] == c["n"] / total
+    # the same game through MCTS / MCTS_Node views (two trees), children lists grow one node per visit
+    log = []
+    kw = dict(MCTS_KW, BUDGET=gk["budget"], TRAINING=True, NEURAL_NET=False)
+    P.play(StubNet("rollout_hash"), kw, max_plies=12, quiet=True,
+           on_search=lambda root, best: log.append((root.n, float(root.w), [(_action(c.state), c.n, float(c.w)) for c in root.children])))
+    for got, want in zip(log, gk["moves"]):
+        assert got == (want["root_n"], want["root_w"], [(c["action"], c["n"], c["w"]) for c in want["children"]])
+    env = C.Checkers(None)
+    M.MCTS(GAME_ENV=env, BUDGET=3, **dict(MCTS_KW, NEURAL_NET=False))
+    root = M.MCTS_Node(env.state)
+    M.MCTS.begin_tree_search(root)
+    assert root.n == 3 and len(root.children) == 3 and len(env.legal_next_states) == 7
+
+
 def test_play_loop_human_input(mods, capsys):
     import play_Checkers as P
     from ckb200.net import StubNet
