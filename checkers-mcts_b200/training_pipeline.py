@@ -46,6 +46,13 @@ def load_blob(filename):
     return blob.astype(np.float32).reshape(-1)
 
 
+def load_model(filename):
+    """Stand-in for ``tensorflow.keras.models.load_model`` in the training phase (train_Checkers.py:163): the saved
+    network (.npy blob or the reference's .h5) as a trainable ``ckb200.train.CheckersNet``."""
+    from ckb200 import train as T
+    return T.CheckersNet(load_blob(filename))
+
+
 def load_training_data(filename):
     with open(filename, 'rb') as file:
         return pickle.load(file)

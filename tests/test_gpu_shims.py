@@ -160,6 +160,32 @@ def test_iteration0_selfplay_without_network(mods, tmp_path, monkeypatch):
     assert root.n == 3 and len(root.children) == 3 and len(env.legal_next_states) == 7
 
 
+def test_train_checkers_iteration_loop(mods, tmp_path, monkeypatch):
+    """train_Checkers.py end to end at toy size: iteration 0 (playout self-play -> first network -> tournament
+    against the untrained one), iteration 1 self-play with the trained network, final round-robin"""
+    import train_Checkers as TC
+    monkeypatch.chdir(tmp_path)
+    small_mcts = {'BUDGET': 16}
+    out = TC.run_iteration(0, SELFPLAY=True, TRAINING=True, EVALUATION=True,
+                           selfplay_kwargs={'NUM_SELFPLAY_GAMES': 3, 'TERMINATE_CNT': 30, 'NUM_CPUS': 2, 'SEED': 11},
+                           mcts_kwargs=small_mcts, training_kwargs={'EPOCHS': 2, 'BATCH_SIZE': 32},
+                           tourney_kwargs={'TOURNEY_GAMES': 2, 'NUM_CPUS': 1, 'SEED': 5}, tourney_mcts_kwargs=small_mcts)
+    assert len(out['data_fns']) == 2 and len(out['history']['loss']) == 2
+    merged = [fn for fn in os.listdir('data/training_data') if 'Data0_' in fn]
+    assert len(merged) == 1                                      # the per-worker files were merged into one
+    data = pickle.load(open('data/training_data/' + merged[0], 'rb'))
+    assert len(data) >= 6 * 20 and all(len(e) == 4 for e in data)
+    for key in ('OLD_NN_FN', 'NEW_NN_FN', 'plot', 'tourney_fn'):
+        assert os.path.isfile(out[key]), key
+    assert 'Model0_' in out['OLD_NN_FN'] and 'Model1_' in out['NEW_NN_FN']
+    assert 'Wins/Losses/Draws' in open(out['tourney_fn'], encoding='utf-8').read()
+    out1 = TC.run_iteration(1, NN_FN=out['NEW_NN_FN'], SELFPLAY=True,
+                            selfplay_kwargs={'NUM_SELFPLAY_GAMES': 2, 'TERMINATE_CNT': 12, 'SEED': 12}, mcts_kwargs=small_mcts)
+    assert len(pickle.load(open(out1['data_fns'], 'rb'))) >= 2 * 12
+    fe = TC.run_final_evaluation([0, 1], tourney_kwargs={'NUM_CPUS': 1, 'SEED': 9}, tourney_mcts_kwargs=small_mcts)
+    assert os.path.isfile(fe) and 'Total' in open(fe, encoding='utf-8').read()
+
+
 def test_play_loop_human_input(mods, capsys):
     import play_Checkers as P
     from ckb200.net import StubNet
