@@ -14,7 +14,8 @@ errors follow the reference:
 Differences that are forced by the device design and stated here rather than hidden:
 ``game_env.neural_net`` must be a device network (``ckb200.net.KerasLikeNet``) or a stub
 (``ckb200.net.StubNet``) -- an arbitrary host ``predict`` object cannot be called from a CUDA
-kernel and there is no CPU fallback; ``CONSTRAINT='time'`` is not supported.  ``NEURAL_NET=False``
+kernel and there is no CPU fallback; with ``CONSTRAINT='time'`` the clock is read every
+``MCTS.time_check_sims`` simulations instead of before each one.  ``NEURAL_NET=False``
 (MCTS.py:78-89,113-115: plain UCT, one child per visit, one random playout per simulation) runs on
 the device as well and needs no network object.
 """
@@ -46,6 +47,7 @@ class MCTS(object):
     # The reference keeps one Python tree per player (play_Checkers.py:128-157, training_pipeline.py:353-377)
     # and a tournament game two more; the least recently created device tree is dropped beyond this many.
     max_trees = 4
+    time_check_sims = 32     # CONSTRAINT='time': simulations between two looks at the clock
     _trees = []
     _tree_serial = 0         # every tree draws from its own random stream
     engine_options = {}      # extra ckb200.lib.make_cfg arguments (pool_cap, compact_always, ...)
@@ -67,9 +69,8 @@ class MCTS(object):
         cls.tau_decay_delay = kwargs['TEMP_DECAY_DELAY']
         cls.seed = kwargs.get('SEED', 1)
         cls.engine_options = dict(kwargs.get('ENGINE_OPTIONS', {}))
-        if cls.constraint != 'rollout':
-            raise ValueError('Invalid MCTS computational constraint!' if cls.constraint != 'time' else
-                             "CONSTRAINT='time' is not supported by the device engine; use 'rollout'")
+        if cls.constraint not in ('rollout', 'time'):
+            raise ValueError('Invalid MCTS computational constraint!')
         cls._close_trees()
 
     # ---- engine plumbing ---------------------------------------------------------------------
@@ -95,7 +96,10 @@ class MCTS(object):
         if kind is None:
             raise TypeError('game_env.neural_net must be a ckb200 device network (ckb200.net.KerasLikeNet) or a '
                             'ckb200.net.StubNet; the search runs on the GPU and cannot call a host predict()')
-        cfg = _L.make_cfg(n_slots=1, budget=cls.budget, device=device, uct_c=cls.uct_c, training=cls.training,
+        # the engine sizes its node pool from the per-search budget; a time-limited search reserves room for
+        # 2048 simulations' worth of expansions between compactions and reports CK_ERR_POOL_OVERFLOW beyond the pool
+        budget = int(cls.budget) if cls.constraint == 'rollout' else 2048
+        cfg = _L.make_cfg(n_slots=1, budget=budget, device=device, uct_c=cls.uct_c, training=cls.training,
                           alpha=cls.alpha, epsilon=cls.epsilon, tau=cls.tau, tau_decay=cls.tau_decay,
                           tau_decay_delay=cls.tau_decay_delay, evaluator=kind, keep_records=False,
                           seed=(cls.seed + 0x9E3779B97F4A7C15 * cls._tree_serial) % (1 << 63), **cls.engine_options)
@@ -154,8 +158,16 @@ class MCTS(object):
         eng = tree.engine
         if cls.verbose:
             print('Starting search!')
-        eng.tree_search(cls.budget)
-        cls.rollout_count = cls.budget
+        if cls.constraint == 'rollout':
+            eng.tree_search(cls.budget)
+            cls.rollout_count = cls.budget
+        else:
+            # CONSTRAINT='time' (MCTS.py:193-195): BUDGET seconds of wall clock, checked between batches of
+            # simulations (the reference checks before every single one)
+            cls.rollout_count = 0
+            while (datetime.now() - start).total_seconds() < cls.budget:
+                eng.tree_search(cls.time_check_sims)
+                cls.rollout_count += cls.time_check_sims
         root_node._children = None
         root_node._number_of_visits, root_node._total_reward, _b = eng.tree_root()
         if cls.verbose:

@@ -153,6 +153,14 @@ def test_iteration0_selfplay_without_network(mods, tmp_path, monkeypatch):
            on_search=lambda root, best: log.append((root.n, float(root.w), [(_action(c.state), c.n, float(c.w)) for c in root.children])))
     for got, want in zip(log, gk["moves"]):
         assert got == (want["root_n"], want["root_w"], [(c["action"], c["n"], c["w"]) for c in want["children"]])
+    # CONSTRAINT='time': BUDGET seconds of searching
+    env = C.Checkers(StubNet("hash"))
+    M.MCTS(GAME_ENV=env, BUDGET=0.2, **dict(MCTS_KW, CONSTRAINT='time'))
+    root = M.MCTS_Node(env.state)
+    M.MCTS.begin_tree_search(root)
+    assert root.n == M.MCTS.rollout_count >= M.MCTS.time_check_sims and root.n % M.MCTS.time_check_sims == 0
+    with pytest.raises(ValueError, match='Invalid MCTS computational constraint'):
+        M.MCTS(GAME_ENV=env, BUDGET=3, **dict(MCTS_KW, CONSTRAINT='memory'))
     env = C.Checkers(None)
     M.MCTS(GAME_ENV=env, BUDGET=3, **dict(MCTS_KW, NEURAL_NET=False))
     root = M.MCTS_Node(env.state)
