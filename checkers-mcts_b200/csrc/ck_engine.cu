@@ -21,6 +21,7 @@
 //   reversed, MCTS.py:72-75), so a PUCT step is one coalesced 16 B x b load.
 //   hist[slot][max_plies+1] ck_pos, path[slot][128] u32, leaves/policy/value per net.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "ck_common.cuh"
@@ -896,8 +897,13 @@ stub_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restrict__
 // (twin of the oracle's cko_hash_choice) so that whole searches can be compared bit for bit.
 __global__ void __launch_bounds__(128)
 playout_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restrict__ n_dev, int kind, uint64_t seed,
-                    uint32_t round, float *__restrict__ value) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+                    uint32_t round, float *__restrict__ value, int lanes_log2) {
+    // playouts diverge from the first ply on, so a warp costs the sum of its lanes' paths: small batches use
+    // only the first 2^lanes_log2 lanes of every warp and spread over more warps (and SMs) instead
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = tid & 31;
+    if (lane >= (1 << lanes_log2)) return;
+    const int row = ((tid >> 5) << lanes_log2) + lane;
     if (row >= *n_dev) return;
     const ck_leaf L = leaves[row];
     ck_pos cur;
@@ -921,9 +927,14 @@ playout_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restric
             if ((k & 3) == 0) rng((uint32_t)(k >> 2), 0u, 0u, 0x504C4159u, r);
             pick = (int)(((uint64_t)r[k & 3] * (uint64_t)cnt) >> 32);
         }
-        ck_pos nxt = cur;
-        gen_moves(cur, PickSink{&nxt, pick}, mask);
-        cur = nxt;
+        // successor number `pick` of the generation order straight from the legal-action planes (no second pass)
+        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+        const Side sd = side_of(cur);
+        uint32_t hop[4];
+        hop_sets(sd, hop);
+        int ms, md;
+        kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);
+        cur = make_child_fast(cur, sd, hop, ms, md, jump);
     }
     value[row] = (float)st;
 }
@@ -1159,8 +1170,17 @@ static int engine_eval(ck_engine *e, int *launches) {
         int kind = d.cfg.evaluator;
         if (k == 1 && d.cfg.evaluator_p2 >= 0) kind = d.cfg.evaluator_p2;
         if (kind == CK_EVAL_ROLLOUT || kind == CK_EVAL_ROLLOUT_HASH) {
-            playout_eval_kernel<<<(d.n_slots + 127) / 128, 128, 0, st>>>(d.leaves[k], &d.ctr->batch_count[k], kind, d.cfg.seed,
-                                                                        d.round, d.value[k]);
+            // about 2048 warps keep every SM busy; fewer lanes per warp below that (measured at 4 Ki / 16 Ki / 64 Ki
+            // games: 2 / 8 / 32 lanes are the fastest, profiles/r1o_uct_playouts.jsonl)
+            static const int lanes_env = getenv("CK_PLAYOUT_LANES_LOG2") ? atoi(getenv("CK_PLAYOUT_LANES_LOG2")) : -1;
+            int lanes_log2 = lanes_env;
+            if (lanes_log2 < 0 || lanes_log2 > 5) {
+                lanes_log2 = 0;
+                while (lanes_log2 < 5 && (d.n_slots >> (lanes_log2 + 1)) >= 2048) ++lanes_log2;
+            }
+            const int64_t threads = (((int64_t)d.n_slots + (1 << lanes_log2) - 1) >> lanes_log2) * 32;
+            playout_eval_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d.leaves[k], &d.ctr->batch_count[k], kind, d.cfg.seed,
+                                                                                  d.round, d.value[k], lanes_log2);
             if (launches) *launches += 1;
         } else if (kind == CK_EVAL_NET) {
             int rc = net_forward_rows(e->net[k], d.leaves[k], d.n_slots, &d.ctr->batch_count[k], d.policy[k], d.value[k], st, launches);

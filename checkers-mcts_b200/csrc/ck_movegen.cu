@@ -221,9 +221,13 @@ rollout_kernel(const uint4 *__restrict__ pos, int64_t n, uint64_t seed, int max_
         if (max_plies > 0 && k >= max_plies) break;
         if ((k & 3) == 0) rng((uint32_t)(k >> 2), 0u, 0u, 0x524F4C4Cu, r);
         const int pick = (int)(((uint64_t)r[k & 3] * (uint64_t)cnt) >> 32);
-        ck_pos nxt = cur;
-        gen_moves(cur, PickSink{&nxt, pick}, mask);
-        cur = nxt;
+        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+        const Side sd = side_of(cur);
+        uint32_t hop[4];
+        hop_sets(sd, hop);
+        int ms, md;
+        kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);       // successor `pick` of the generation order
+        cur = make_child_fast(cur, sd, hop, ms, md, jump);
         ++k;
     }
     if (outcome) outcome[i] = (uint8_t)st;
