@@ -1,5 +1,7 @@
 """Secondary BASELINE.json configurations on one GPU (parity-test cases, not bench lines):
 
+  cfg1  ONE self-play game at 50 sims/move (the reference's own CPU-runnable case) played to the end through the
+        engine: latency of a lock-step round with a batch of one position
   cfg3  4096 concurrent self-play games per GPU at 800 sims/move (the per-GPU share of the
         32768-game / 8-GPU configuration), a bounded number of lock-step rounds
   cfg5  arena: evaluator games between two independent random-init networks (seeds 0 and 1), net A
@@ -31,6 +33,19 @@ def main():
         net = L.Net(0)
         net.set_weights(N.random_init_blob(seed))
         nets.append(net)
+
+    # ---- cfg1 ----
+    eng = L.Engine(L.make_cfg(n_slots=1, budget=50, training=True, terminate_cnt=200, evaluator="net", keep_records=True,
+                              uct_c=4.0, alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=1))
+    eng.set_net(0, nets[0])
+    eng.selfplay(1)                                   # warm-up game
+    st = eng.selfplay(1)
+    g = eng.games()
+    print(json.dumps({"workload": "cfg1: 1 self-play game, 50 sims/move, random-init net, TERMINATE_CNT 200",
+                      "sims_per_sec": st["sims"] / (st["gpu_ms"] / 1e3), "games_per_sec": 1e3 / st["gpu_ms"],
+                      "ms_per_round": st["gpu_ms"] / max(st["steps"], 1), "sims": st["sims"], "gpu_ms": st["gpu_ms"],
+                      "plies": int(g["move_count"][0])}), flush=True)
+    eng.close()
 
     # ---- cfg3 ----
     eng = L.Engine(L.make_cfg(n_slots=4096, budget=800, training=True, terminate_cnt=200, evaluator="net", keep_records=True,
