@@ -65,6 +65,7 @@ def _load():
     L.ck_movegen.argtypes = [C.c_int, vp, i64, i32, vp, vp, vp, vp, vp]
     L.ck_movegen_device.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp]
     L.ck_rollout.argtypes = [C.c_int, vp, i64, u64, i32, vp, vp]
+    L.ck_rollout_device.argtypes = [vp, i64, u64, i32, vp, vp, vp]
     L.ck_net_create.argtypes = [C.c_int]
     L.ck_net_create.restype = vp
     L.ck_net_destroy.argtypes = [vp]

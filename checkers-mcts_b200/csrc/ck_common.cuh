@@ -73,6 +73,18 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+// uniform successor choice of a playout: one Philox block serves four plies (np.random.randint, MCTS.py:141)
+struct PhiloxChoice {
+    Philox rng;
+    uint32_t tag;
+    mutable uint32_t r[4];
+    template <typename Pos>
+    __host__ __device__ int operator()(const Pos &, int ply, int cnt) const {
+        if ((ply & 3) == 0) rng((uint32_t)(ply >> 2), 0u, 0u, tag, r);
+        return (int)(((uint64_t)r[ply & 3] * (uint64_t)cnt) >> 32);
+    }
+};
+
 // uniform in (0,1] from two 32-bit words (53 bits)
 __host__ __device__ inline double u01(uint32_t a, uint32_t b) {
     const uint64_t v = (((uint64_t)a << 32) | b) >> 11;

@@ -850,10 +850,6 @@ __global__ void sum_slots_kernel(const EngineDev E, unsigned long long *out_sims
 }
 
 // ---- stub evaluators (deterministic parity tests; twins of the oracle's cko_eval_*) ----------
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
-    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
-    return h;
-}
 __global__ void __launch_bounds__(128)
 stub_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restrict__ n_dev, int kind,
                  float *__restrict__ policy, float *__restrict__ value) {
@@ -908,33 +904,11 @@ playout_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restric
     const ck_leaf L = leaves[row];
     ck_pos cur;
     cur.p1 = L.p1; cur.p2 = L.p2; cur.k = L.k; cur.meta = L.mask[0];
-    const Philox rng(mix64(seed ^ mix64(((uint64_t)(L.info >> 16) << 32) | round)));
-    uint32_t r[4];
     int st;
-    for (int k = 0;; ++k) {
-        uint32_t mask[8];
-        const int cnt = gen_moves(cur, NullSink{}, mask);
-        st = outcome_of(cur, cnt > 0, nullptr);
-        if (st != CK_ONGOING) break;
-        int pick;
-        if (kind == CK_EVAL_ROLLOUT_HASH) {
-            uint32_t h = mix32(cur.p1 ^ 0x9e3779b9u ^ ((L.info >> 16) * 0x9E3779B1u));      // salted with the game tag
-            h = mix32(h ^ cur.p2);
-            h = mix32(h ^ cur.k);
-            h = mix32(h ^ (cur.meta & 1u));
-            pick = (int)(h % (uint32_t)cnt);
-        } else {
-            if ((k & 3) == 0) rng((uint32_t)(k >> 2), 0u, 0u, 0x504C4159u, r);
-            pick = (int)(((uint64_t)r[k & 3] * (uint64_t)cnt) >> 32);
-        }
-        // successor number `pick` of the generation order straight from the legal-action planes (no second pass)
-        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
-        const Side sd = side_of(cur);
-        uint32_t hop[4];
-        hop_sets(sd, hop);
-        int ms, md;
-        kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);
-        cur = make_child_fast(cur, sd, hop, ms, md, jump);
+    if (kind == CK_EVAL_ROLLOUT_HASH) {
+        st = play_out(cur, 0, HashChoice{L.info >> 16}, nullptr);            // salted with the game tag
+    } else {
+        st = play_out(cur, 0, PhiloxChoice{Philox(mix64(seed ^ mix64(((uint64_t)(L.info >> 16) << 32) | round))), 0x504C4159u}, nullptr);
     }
     value[row] = (float)st;
 }

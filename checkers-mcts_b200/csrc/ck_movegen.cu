@@ -210,26 +210,8 @@ rollout_kernel(const uint4 *__restrict__ pos, int64_t n, uint64_t seed, int max_
     const uint4 v = __ldg(pos + i);
     ck_pos cur;
     cur.p1 = v.x; cur.p2 = v.y; cur.k = v.z; cur.meta = v.w;
-    const Philox rng(mix64(seed ^ mix64((uint64_t)i)));
-    int k = 0, st;
-    uint32_t r[4];
-    for (;;) {
-        uint32_t mask[8];
-        const int cnt = gen_moves(cur, NullSink{}, mask);
-        st = outcome_of(cur, cnt > 0, nullptr);
-        if (st != CK_ONGOING) break;
-        if (max_plies > 0 && k >= max_plies) break;
-        if ((k & 3) == 0) rng((uint32_t)(k >> 2), 0u, 0u, 0x524F4C4Cu, r);
-        const int pick = (int)(((uint64_t)r[k & 3] * (uint64_t)cnt) >> 32);
-        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
-        const Side sd = side_of(cur);
-        uint32_t hop[4];
-        hop_sets(sd, hop);
-        int ms, md;
-        kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);       // successor `pick` of the generation order
-        cur = make_child_fast(cur, sd, hop, ms, md, jump);
-        ++k;
-    }
+    int k = 0;
+    const int st = play_out(cur, max_plies, PhiloxChoice{Philox(mix64(seed ^ mix64((uint64_t)i))), 0x524F4C4Cu}, &k);
     if (outcome) outcome[i] = (uint8_t)st;
     if (plies) plies[i] = k;
 }
@@ -403,6 +385,16 @@ int ck_rollout(int device, const ck_pos *pos, int64_t n, uint64_t seed, int32_t 
     if (outcome) CK_TRY(cudaMemcpy(outcome, d_out, n, cudaMemcpyDeviceToHost));
     if (plies) CK_TRY(cudaMemcpy(plies, d_pl, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     cleanup();
+    return CK_OK;
+}
+
+int ck_rollout_device(const ck_pos *d_pos, int64_t n, uint64_t seed, int32_t max_plies,
+                      uint8_t *d_outcome, int32_t *d_plies, void *stream) {
+    if (n < 0 || !d_pos) return fail(CK_ERR_ARG, "ck_rollout_device: bad arguments");
+    if (n == 0) return CK_OK;
+    rollout_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4 *)d_pos, n, seed, max_plies,
+                                                                                 d_outcome, d_plies);
+    CK_CUDA(cudaGetLastError());
     return CK_OK;
 }
 

@@ -344,6 +344,48 @@ CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, in
     return make_child(p, sd, s, d, jump);
 }
 
+// ---- playouts (MCTS.default_policy without a net, MCTS.py:132-143) ------------------------------------
+// One generation pass per ply: `choose(position, ply, n_legal)` names the successor in generation order
+// and it is built from the legal-action planes.  Returns the CK_* outcome; *plies = plies played.
+template <typename Choose>
+CK_HD int play_out(ck_pos cur, int max_plies, const Choose &choose, int *plies) {
+    int k = 0, st;
+    for (;;) {
+        uint32_t mask[8];
+        const int cnt = gen_moves(cur, NullSink{}, mask);
+        st = outcome_of(cur, cnt > 0, nullptr);
+        if (st != CK_ONGOING) break;
+        if (max_plies > 0 && k >= max_plies) break;
+        const int pick = choose(cur, k, cnt);
+        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+        const Side sd = side_of(cur);
+        uint32_t hop[4];
+        hop_sets(sd, hop);
+        int ms, md;
+        kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);
+        cur = make_child_fast(cur, sd, hop, ms, md, jump);
+        ++k;
+    }
+    if (plies) *plies = k;
+    return st;
+}
+
+// deterministic stand-in for the uniform choice (parity tests; twin of the oracle's cko_hash_choice)
+CK_HD uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+struct HashChoice {
+    uint32_t salt;
+    CK_HD int operator()(const ck_pos &p, int, int cnt) const {
+        uint32_t h = mix32(p.p1 ^ 0x9e3779b9u ^ (salt * 0x9E3779B1u));
+        h = mix32(h ^ p.p2);
+        h = mix32(h ^ p.k);
+        h = mix32(h ^ (p.meta & 1u));
+        return (int)(h % (uint32_t)cnt);
+    }
+};
+
 CK_HD ck_pos start_position() {
     ck_pos p;
     p.p1 = 0x00000FFFu; p.p2 = 0xFFF00000u; p.k = 0; p.meta = 0;

@@ -77,6 +77,9 @@ int ck_movegen_csr_device(const ck_pos *d_pos, int64_t n, ck_pos *d_children, in
  * unlimited. */
 int ck_rollout(int device, const ck_pos *pos, int64_t n, uint64_t seed, int32_t max_plies,
                uint8_t *outcome, int32_t *plies);
+/* the same on device-resident buffers, asynchronously on `stream` (the device the buffers live on must be current) */
+int ck_rollout_device(const ck_pos *d_pos, int64_t n, uint64_t seed, int32_t max_plies,
+                      uint8_t *d_outcome, int32_t *d_plies, void *stream);
 
 /* ---- K3: policy/value network ------------------------------------------------------
  * Replaces neural_net.predict behind Checkers.predict (Checkers.py:425-438); the

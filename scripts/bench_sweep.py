@@ -103,15 +103,35 @@ def main():
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         ms = float(np.median(times))
-        # random playouts (K4)
+        # random playouts (K4): host call once (results + end-to-end time), kernel timed on the device
         t0 = time.time()
         outcome, plies = L.rollout(pos, seed=1)
         roll_s = time.time() - t0
+        d_outc = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        d_pl = torch.zeros(n, dtype=torch.int32, device="cuda")
+
+        def launch_rollout():
+            L.check(lib.ck_rollout_device(C.c_void_p(d_pos.data_ptr()), n, 1, 0, C.c_void_p(d_outc.data_ptr()),
+                                          C.c_void_p(d_pl.data_ptr()), C.c_void_p(stream)))
+        launch_rollout()
+        torch.cuda.synchronize()
+        assert (d_pl.cpu().numpy() == plies).all() and (d_outc.cpu().numpy() == outcome).all()
+        times = []
+        for _ in range(max(3, args.iters // 4)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            launch_rollout()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        roll_ms = float(np.median(times))
         line = {"workload": "cfg4 movegen/rollout sweep", "positions": n, "movegen_ms": ms, "movegen_strided_ms": ms_strided,
                 "layout": "packed CSR (ck_movegen_csr_device; timing includes the workspace memset); strided = [n][48] ck_movegen_device",
                 "positions_per_sec": n / (ms / 1e3), "mean_children": b,
                 "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
                              "frac": bytes_alg / (ms / 1e3) / 1e9 / hbm, "alg_bytes_per_position": bytes_alg / n},
+                "playout_kernel_ms": roll_ms, "playouts_per_sec": n / (roll_ms / 1e3),
+                "plies_per_sec": float(plies.sum()) / (roll_ms / 1e3),
                 "playouts_per_sec_e2e": n / roll_s, "playout_plies_mean": float(plies.mean()),
                 "plies_per_sec_e2e": float(plies.sum()) / roll_s}
         if lg == 10:

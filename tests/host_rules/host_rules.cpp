@@ -39,5 +39,9 @@ extern "C" int ckh_movegen_fast(const ck_pos *pos, ck_pos *children) {
         }
     return n;
 }
+// the playout loop of K4 / playout_eval_kernel with the hashed successor choice (oracle: cko_hash_playout)
+extern "C" int ckh_hash_playout(const ck_pos *pos, uint32_t salt, int *plies) {
+    return ck::play_out(*pos, 0, ck::HashChoice{salt}, plies);
+}
 extern "C" int ckh_status(const ck_pos *pos, int *plane5) { return ck::status_of(*pos, plane5); }
 extern "C" void ckh_start(ck_pos *p) { *p = ck::start_position(); }

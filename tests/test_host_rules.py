@@ -31,6 +31,8 @@ def hr():
     L.ckh_kth.restype = None
     L.ckh_status.argtypes = [C.POINTER(O.Pos), C.POINTER(C.c_int)]
     L.ckh_status.restype = C.c_int
+    L.ckh_hash_playout.argtypes = [C.POINTER(O.Pos), C.c_uint32, C.POINTER(C.c_int)]
+    L.ckh_hash_playout.restype = C.c_int
     return L
 
 
@@ -97,3 +99,25 @@ def test_host_rules_synthetic(hr):
         meta = codec.make_meta(rng.randint(2), rng.randint(0, 90), 0, 0, rng.randint(0, 200))
         pos = (p1, p2, k, meta)
         assert _host_movegen(hr, pos) == O.movegen(pos)
+
+
+def test_host_playouts_match_oracle(hr):
+    """ck::play_out (the loop of K4 `rollout_kernel` and of `playout_eval_kernel`: one generation pass per ply,
+    successor built from the legal-action planes) with the hashed choice against the oracle's playout, from
+    positions all over random games -- outcome and length, including the draw rule's counters"""
+    rng = np.random.RandomState(11)
+    seen = set()
+    for game in range(60):
+        pos = O.start_position()
+        for _ply in range(rng.randint(0, 120)):
+            kids, _mask, status, _p5 = O.movegen(pos)
+            if status != 0:
+                break
+            pos = kids[rng.randint(len(kids))]
+        salt = game % 5
+        plies = C.c_int()
+        got = hr.ckh_hash_playout(C.byref(O.Pos(*[int(v) for v in pos])), salt, C.byref(plies))
+        want = O.hash_playout(pos, salt)
+        assert (got, plies.value) == want, (pos, salt)
+        seen.add(got)
+    assert seen >= {1, 2}                                  # both colours win somewhere in the sample
