@@ -347,25 +347,29 @@ CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, in
 // ---- playouts (MCTS.default_policy without a net, MCTS.py:132-143) ------------------------------------
 // One generation pass per ply: `choose(position, ply, n_legal)` names the successor in generation order
 // and it is built from the legal-action planes.  Returns the CK_* outcome; *plies = plies played.
+constexpr int kPlayMoved = -1;
+// one ply: kPlayMoved after moving `cur` on, otherwise the playout is over and the CK_* outcome is returned
+// (CK_ONGOING when it was cut off at max_plies)
+template <typename Choose>
+CK_HD int play_step(ck_pos &cur, int k, int max_plies, const Choose &choose) {
+    uint32_t mask[8];
+    const int cnt = gen_moves(cur, NullSink{}, mask);
+    const int st = outcome_of(cur, cnt > 0, nullptr);
+    if (st != CK_ONGOING || (max_plies > 0 && k >= max_plies)) return st;
+    const int pick = choose(cur, k, cnt);
+    const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
+    const Side sd = side_of(cur);
+    uint32_t hop[4];
+    hop_sets(sd, hop);
+    int ms, md;
+    kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);
+    cur = make_child_fast(cur, sd, hop, ms, md, jump);
+    return kPlayMoved;
+}
 template <typename Choose>
 CK_HD int play_out(ck_pos cur, int max_plies, const Choose &choose, int *plies) {
     int k = 0, st;
-    for (;;) {
-        uint32_t mask[8];
-        const int cnt = gen_moves(cur, NullSink{}, mask);
-        st = outcome_of(cur, cnt > 0, nullptr);
-        if (st != CK_ONGOING) break;
-        if (max_plies > 0 && k >= max_plies) break;
-        const int pick = choose(cur, k, cnt);
-        const bool jump = (mask[4] | mask[5] | mask[6] | mask[7]) != 0;
-        const Side sd = side_of(cur);
-        uint32_t hop[4];
-        hop_sets(sd, hop);
-        int ms, md;
-        kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);
-        cur = make_child_fast(cur, sd, hop, ms, md, jump);
-        ++k;
-    }
+    while ((st = play_step(cur, k, max_plies, choose)) == kPlayMoved) ++k;
     if (plies) *plies = k;
     return st;
 }
