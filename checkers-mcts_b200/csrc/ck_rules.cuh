@@ -299,42 +299,37 @@ CK_HD int gen_moves(const ck_pos &p, const Sink &sink, uint32_t mask[8]) {
 // where one lane per SUCCESSOR (instead of per position) keeps warps converged and stores coalesced.
 // (source square, direction) of the k-th entry of that list
 CK_HD void kth_move(const Side &sd, const uint32_t use[4], bool jump, int k, int *s_out, int *d_out) {
+    // One converged path for men and kings (a warp of playouts or of successors mixes both all the time) and
+    // constant indices into use[] only: the ordered direction slots of the phase the k-th entry falls in are
+    // selected up front -- men: their two forward directions (order_dir), kings: UL,UR,BL,BR or UL,BL,UR,BR.
     const uint32_t kings = sd.kings;
-    const int da = order_dir(false, jump, sd.player, 0), db = order_dir(false, jump, sd.player, 1);
-    const uint32_t ua = use[da] & ~kings, ub = use[db] & ~kings;
+    const bool p0 = sd.player == 0;
+    const uint32_t f_lo = p0 ? use[2] : use[0], f_hi = p0 ? use[3] : use[1];    // forward-left / forward-right
+    const int base = p0 ? 2 : 0;
+    const uint32_t ua = (jump ? f_lo : f_hi) & ~kings, ub = (jump ? f_hi : f_lo) & ~kings;
     const int men_total = popc32(ua) + popc32(ub);
-    int s = 0, d;
-    if (k < men_total) {
+    const bool kp = k >= men_total;                                             // the entry is a king's
+    k -= kp ? men_total : 0;
+    const uint32_t m0 = kp ? (use[0] & kings) : ua;
+    const uint32_t m1 = kp ? ((jump ? use[2] : use[1]) & kings) : ub;
+    const uint32_t m2 = kp ? ((jump ? use[1] : use[2]) & kings) : 0u;
+    const uint32_t m3 = kp ? (use[3] & kings) : 0u;
+    const int e0 = kp ? 0 : (jump ? base : base + 1), e1 = kp ? (jump ? 2 : 1) : (jump ? base + 1 : base);
+    const int e2 = jump ? 1 : 2;
+    int s = 0;
 #pragma unroll
-        for (int step = 16; step; step >>= 1) {
-            const uint32_t below = (1u << (s + step)) - 1u;
-            if (popc32(ua & below) + popc32(ub & below) <= k) s += step;
-        }
-        const uint32_t below = (1u << s) - 1u;
-        const int r = k - popc32(ua & below) - popc32(ub & below);
-        d = (r == 0 && ((ua >> s) & 1u)) ? da : db;
-    } else {
-        k -= men_total;
-        uint32_t uk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) uk[i] = use[order_dir(true, jump, sd.player, i)] & kings;
-#pragma unroll
-        for (int step = 16; step; step >>= 1) {
-            const uint32_t below = (1u << (s + step)) - 1u;
-            if (popc32(uk[0] & below) + popc32(uk[1] & below) + popc32(uk[2] & below) + popc32(uk[3] & below) <= k) s += step;
-        }
-        const uint32_t below = (1u << s) - 1u;
-        int r = k - popc32(uk[0] & below) - popc32(uk[1] & below) - popc32(uk[2] & below) - popc32(uk[3] & below);
-        d = order_dir(true, jump, sd.player, 3);
-#pragma unroll
-        for (int i = 2; i >= 0; --i) {
-            // number of this king's directions before slot i
-            int before = 0;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) if (q < i) before += (int)((uk[q] >> s) & 1u);
-            if (((uk[i] >> s) & 1u) && before == r) d = order_dir(true, jump, sd.player, i);
-        }
+    for (int step = 16; step; step >>= 1) {
+        const uint32_t below = (1u << (s + step)) - 1u;
+        if (popc32(m0 & below) + popc32(m1 & below) + popc32(m2 & below) + popc32(m3 & below) <= k) s += step;
     }
+    const uint32_t below = (1u << s) - 1u;
+    const int r = k - popc32(m0 & below) - popc32(m1 & below) - popc32(m2 & below) - popc32(m3 & below);
+    // the r-th of this piece's directions that are set, in slot order
+    const int b0 = (int)((m0 >> s) & 1u), b1 = (int)((m1 >> s) & 1u), b2 = (int)((m2 >> s) & 1u);
+    int d = 3;
+    if (b2 && b0 + b1 == r) d = e2;
+    if (b1 && b0 == r) d = e1;
+    if (b0 && r == 0) d = e0;
     *s_out = s; *d_out = d;
 }
 CK_HD ck_pos kth_successor(const ck_pos &p, const uint32_t use[4], bool jump, int k) {
@@ -362,7 +357,8 @@ CK_HD int play_step(ck_pos &cur, int k, int max_plies, const Choose &choose) {
     uint32_t hop[4];
     hop_sets(sd, hop);
     int ms, md;
-    kth_move(sd, jump ? mask + 4 : mask, jump, pick, &ms, &md);
+    const uint32_t use[4] = {jump ? mask[4] : mask[0], jump ? mask[5] : mask[1], jump ? mask[6] : mask[2], jump ? mask[7] : mask[3]};
+    kth_move(sd, use, jump, pick, &ms, &md);
     cur = make_child_fast(cur, sd, hop, ms, md, jump);
     return kPlayMoved;
 }
