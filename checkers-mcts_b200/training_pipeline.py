@@ -213,13 +213,15 @@ class generate_Checkers_data(object):
         total = self.NUM_SELFPLAY_GAMES * self.num_cpus
         cfg = _engine_cfg(self.mcts_kwargs, min(total, self.max_slots), self.TERMINATE_CNT,
                           spec if isinstance(spec, str) else "net", device=self.device, seed=self.seed)
-        eng = _L.Engine(cfg)
-        net = _attach(eng, 0, spec, self.device)
-        self.stats = eng.selfplay(total)
-        recs, games = eng.records(), eng.games()
-        eng.close()
-        if net is not None:
-            net.close()
+        eng, net = _L.Engine(cfg), None
+        try:
+            net = _attach(eng, 0, spec, self.device)
+            self.stats = eng.selfplay(total)
+            recs, games = eng.records(), eng.games()
+        finally:                                          # device memory goes back also when a run fails
+            eng.close()
+            if net is not None:
+                net.close()
         names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
         for g in games:
             print('{} after {} moves!'.format(names[int(g["outcome"])], int(g["move_count"])))
@@ -260,14 +262,17 @@ class tournament_Checkers(object):
         seed = None if self.seed is None else self.seed + process_num
         cfg = _engine_cfg(self.mcts_kwargs, min(self.NUM_GAMES, 4096), 0, ev1, ev2, arena=True, keep_records=False,
                           device=self.device, seed=seed)
-        eng = _L.Engine(cfg)
-        nets = [_attach(eng, 0, s1, self.device), _attach(eng, 1, s2, self.device)]
-        self.stats = eng.arena(self.NUM_GAMES)
-        games = eng.games()
-        eng.close()
-        for n in nets:
-            if n is not None:
-                n.close()
+        eng, nets = _L.Engine(cfg), []
+        try:
+            nets.append(_attach(eng, 0, s1, self.device))
+            nets.append(_attach(eng, 1, s2, self.device))
+            self.stats = eng.arena(self.NUM_GAMES)
+            games = eng.games()
+        finally:
+            eng.close()
+            for n in nets:
+                if n is not None:
+                    n.close()
         names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
         rows = []
         for g in games:

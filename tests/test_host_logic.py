@@ -214,3 +214,41 @@ def test_training_step_matches_reference_recipe(tmp_path, monkeypatch):
         for it in (0, 7, 40, 63, 80, 131):
             clr.clr_iterations = float(it)
             assert abs(float(clr.clr()) - T.clr_triangular(it, 5e-5, 1e-2, 40)) < 1e-15
+
+
+def test_play_checkers_move_listing_and_record_q():
+    """host-side pieces of the console game and of the playout-mode records: the (from, to) listing of legal
+    moves for plain moves, jumps and promotions of either side (play_Checkers.py:62-84), and the exact
+    int / int quotient the reference records as q when NEURAL_NET=False"""
+    import play_Checkers as P
+    rng = np.random.RandomState(4)
+    seen_jump = seen_promo = False
+    for _game in range(30):
+        pos = O.start_position()
+        for _ply in range(90):
+            kids, _mask, status, _p5 = O.movegen(pos)
+            if status != 0:
+                break
+            state = codec.decode_state(pos)
+            listing = P.states_to_piece_positions(state, [codec.decode_state(k) for k in kids])
+            assert len(listing) == len(kids)
+            mover = (0, 1) if state[4, 0, 0] == 0 else (2, 3)
+            for (src, dst), kid in zip(listing, kids):
+                ks = codec.decode_state(kid)
+                (sx, sy), (dx, dy) = (src[0] - 1, src[1] - 1), (dst[0] - 1, dst[1] - 1)
+                assert state[mover[0], sx, sy] + state[mover[1], sx, sy] == 1       # a piece of the mover stood there
+                assert ks[mover[0], dx, dy] + ks[mover[1], dx, dy] == 1             # and stands here now
+                assert ks[mover[0], sx, sy] + ks[mover[1], sx, sy] == 0
+                assert abs(dx - sx) == abs(dy - sy) and abs(dx - sx) in (1, 2)
+                seen_jump |= abs(dx - sx) == 2
+                seen_promo |= bool(state[mover[0], sx, sy] == 1 and ks[mover[1], dx, dy] == 1)
+            pos = kids[rng.randint(len(kids))]
+    assert seen_jump and seen_promo
+    rec = np.zeros(1, dtype=[("pos", np.uint32, 4), ("mask", np.uint32, 8), ("plane5", np.int32), ("n_children", np.int32),
+                             ("action", np.uint16, 48), ("visits", np.uint32, 48), ("q", np.float32), ("z", np.int32),
+                             ("root_n", np.uint32), ("root_w", np.float32)])[0]
+    rec["pos"] = O.start_position()
+    rec["n_children"], rec["action"][:2], rec["visits"][:2] = 2, (149, 151), (70, 80)
+    rec["root_n"], rec["root_w"], rec["q"] = 150, -7.0, np.float32(7.0) / np.float32(150.0)     # flipped to the root player's view
+    assert R.to_reference(rec, playouts=True)[2] == 7 / 150 and type(R.to_reference(rec, playouts=True)[2]) is float
+    assert R.to_reference(rec)[2] == np.float32(7.0) / np.float32(150.0)
