@@ -19,6 +19,7 @@ from datetime import datetime
 import numpy as np
 from tabulate import tabulate
 
+from ckb200 import dist as _D
 from ckb200 import lib as _L
 from ckb200 import net as _N
 from ckb200 import records as _R
@@ -179,6 +180,22 @@ def _engine_cfg(mcts_kwargs, n_slots, terminate_cnt, evaluator, evaluator_p2=Non
                        arena=arena, keep_records=keep_records, game_id_base=game_id_base, game_id_stride=game_id_stride)
 
 
+def _np_empty(dtype):
+    return np.zeros(0, dtype=dtype)
+
+
+def _dist_setup(device, seed):
+    """(rank, world, CUDA device of this process, seed shared by all ranks)"""
+    rank, world, local_rank = _D.rank_world()
+    if world > 1:
+        device = local_rank
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little") >> 1      # np.random.seed() from OS entropy (:341)
+    if world > 1:
+        seed = _D.broadcast_int(seed, rank, world, device="cuda:%d" % device)
+    return rank, world, device, seed
+
+
 def _attach(engine, which, spec, device):
     if isinstance(spec, str):
         return None
@@ -209,19 +226,34 @@ class generate_Checkers_data(object):
         # NEURAL_NET=False is the reference's iteration-0 mode (train_Checkers.py:78): plain UCT with random
         # playouts, no network involved (the reference still loads NN_FN there and never calls it)
         playouts = not self.mcts_kwargs.get('NEURAL_NET', True)
-        spec = self.mcts_kwargs.get('PLAYOUT_EVALUATOR', 'rollout') if playouts else load_blob(self.nn_fn)
         total = self.NUM_SELFPLAY_GAMES * self.num_cpus
-        cfg = _engine_cfg(self.mcts_kwargs, min(total, self.max_slots), self.TERMINATE_CNT,
-                          spec if isinstance(spec, str) else "net", device=self.device, seed=self.seed)
-        eng, net = _L.Engine(cfg), None
-        try:
-            net = _attach(eng, 0, spec, self.device)
-            self.stats = eng.selfplay(total)
-            recs, games = eng.records(), eng.games()
-        finally:                                          # device memory goes back also when a run fails
-            eng.close()
-            if net is not None:
-                net.close()
+        # under torchrun (one process per GPU) the games shard by index over the ranks, game g on rank g mod world,
+        # every rank plays its share with the same seed (a game's random stream depends on its global index only)
+        # and rank 0 pools the records: the files are the same as from a single process
+        rank, world, device, seed = _dist_setup(self.device, self.seed)
+        spec = self.mcts_kwargs.get('PLAYOUT_EVALUATOR', 'rollout') if playouts else load_blob(self.nn_fn)
+        base, stride, n_local = _D.shard(total, rank, world)
+        recs, games = _np_empty(_L.RECORD_DTYPE), _np_empty(_L.GAME_DTYPE)
+        if n_local > 0:
+            cfg = _engine_cfg(self.mcts_kwargs, min(n_local, self.max_slots), self.TERMINATE_CNT,
+                              spec if isinstance(spec, str) else "net", device=device, seed=seed,
+                              game_id_base=base, game_id_stride=stride)
+            eng, net = _L.Engine(cfg), None
+            try:
+                net = _attach(eng, 0, spec, device)
+                self.stats = eng.selfplay(n_local)
+                recs, games = eng.records(), eng.games()
+            finally:                                      # device memory goes back also when a run fails
+                eng.close()
+                if net is not None:
+                    net.close()
+        if world > 1:
+            recs = _D.gather_records(recs, rank, world, device="cuda:%d" % device)
+            games = _D.gather_records(games, rank, world, device="cuda:%d" % device)
+            if rank != 0:
+                return []
+        recs = recs[np.argsort(recs["game"], kind="stable")]       # game by game, plies in order
+        games = games[np.argsort(games["game"], kind="stable")]
         names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
         for g in games:
             print('{} after {} moves!'.format(names[int(g["outcome"])], int(g["move_count"])))
@@ -259,20 +291,28 @@ class tournament_Checkers(object):
         s1, s2 = load_blob(self.nn1_fn), load_blob(self.nn2_fn)
         ev1 = s1 if isinstance(s1, str) else "net"
         ev2 = s2 if isinstance(s2, str) else "net"
-        seed = None if self.seed is None else self.seed + process_num
-        cfg = _engine_cfg(self.mcts_kwargs, min(self.NUM_GAMES, 4096), 0, ev1, ev2, arena=True, keep_records=False,
-                          device=self.device, seed=seed)
+        rank, world, device, seed = _dist_setup(self.device, None if self.seed is None else self.seed + process_num)
+        if self.NUM_GAMES % world:
+            raise ValueError('TOURNEY_GAMES must be a multiple of the number of ranks')
+        base, stride, n_local = _D.shard(self.NUM_GAMES, rank, world)       # games shard over the ranks as in self-play
+        cfg = _engine_cfg(self.mcts_kwargs, min(n_local, 4096), 0, ev1, ev2, arena=True, keep_records=False,
+                          device=device, seed=seed, game_id_base=base, game_id_stride=stride)
         eng, nets = _L.Engine(cfg), []
         try:
-            nets.append(_attach(eng, 0, s1, self.device))
-            nets.append(_attach(eng, 1, s2, self.device))
-            self.stats = eng.arena(self.NUM_GAMES)
+            nets.append(_attach(eng, 0, s1, device))
+            nets.append(_attach(eng, 1, s2, device))
+            self.stats = eng.arena(n_local)
             games = eng.games()
         finally:
             eng.close()
             for n in nets:
                 if n is not None:
                     n.close()
+        if world > 1:
+            games = _D.gather_records(games, rank, world, device="cuda:%d" % device)
+            if rank != 0:
+                return []
+        games = games[np.argsort(games["game"], kind="stable")]
         names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
         rows = []
         for g in games:
@@ -284,6 +324,8 @@ class tournament_Checkers(object):
         game_outcomes = []
         for proc in range(self.num_cpus):                 # each worker plays its own TOURNEY_GAMES (:491-494)
             game_outcomes.extend(self._start_tournament(proc))
+        if not game_outcomes:                             # a rank other than 0 of a multi-GPU run
+            return None
         filename = self._save_tourney_results(game_outcomes)
         print('Tournament over!  View results in tournament folder!')
         return filename
@@ -343,6 +385,8 @@ class final_evaluation(object):
             for old_nn_fn in model_fn_list:
                 game_outcomes.extend(self._wrapper_func(new_nn_fn, old_nn_fn))
             self.game_outcomes.append(game_outcomes)
+        if _D.rank_world()[0] != 0:                       # rank 0 holds the pooled results of a multi-GPU run
+            return None
         filename = self._parse_tourney_results()
         print('Final evaluation over!  View results in final_eval folder!')
         return filename

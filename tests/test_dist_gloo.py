@@ -24,6 +24,11 @@ def _worker(rank, world, port, q):
         for k in range(3):
             recs[i * 3 + k] = (base + i * stride, k, rank + 0.5, [rank, i, k, 7, 9])
     out = D.gather_records(recs, rank, world)
+    # iteration start: the weights and the seed of rank 0 reach every rank
+    assert D.rank_world()[:2] == (rank, world)
+    blob = D.broadcast_weights(np.arange(1000, dtype=np.float32) * 0.5 if rank == 0 else None, rank, world)
+    assert blob.dtype == np.float32 and (blob == np.arange(1000, dtype=np.float32) * 0.5).all()
+    assert D.broadcast_int(0x1234567890ABCDEF >> 1 if rank == 0 else 7, rank, world) == 0x1234567890ABCDEF >> 1
     if rank == 0:
         q.put((n_local, out.tobytes(), out.dtype.descr))
     else:
