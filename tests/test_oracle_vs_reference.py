@@ -1,5 +1,7 @@
 """Runs the unmodified reference next to the oracle (build container only; skipped where
 /root/reference is not mounted -- the committed golden vectors cover that case)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -71,3 +73,41 @@ def test_tree_search_matches_reference_from_midgame():
         got = t.root_children()
         assert [(c["n"], float(c["w"]), float(c["p"])) for c in got] == \
                [(c.n, float(c.w), float(c.p)) for c in root.children]
+
+
+def _dict_literals(path, names):
+    """dict literals assigned to `names` in a reference script, without executing it; values that are plain
+    names (TRAINING_ITERATION, NN_FN, ...) come back as the name in angle brackets"""
+    import ast
+    out = {}
+    for node in ast.walk(ast.parse(open(path).read())):
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) \
+                and node.targets[0].id in names and isinstance(node.value, ast.Dict):
+            d = {}
+            for k, v in zip(node.value.keys, node.value.values):
+                d[ast.literal_eval(k)] = '<%s>' % v.id if isinstance(v, ast.Name) else ast.literal_eval(v)
+            out[node.targets[0].id] = d
+    return out
+
+
+@pytest.mark.needs_reference
+def test_driver_defaults_equal_the_reference_scripts():
+    """train_Checkers.py / play_Checkers.py of this package carry the reference scripts' settings
+    (train_Checkers.py:80-127,179-201; play_Checkers.py:88-103) as defaults"""
+    import play_Checkers as P
+    import train_Checkers as TC
+    ref = _dict_literals(os.path.join(H.REFERENCE_DIR, "train_Checkers.py"),
+                         ("selfplay_kwargs", "mcts_kwargs", "training_kwargs", "tourney_kwargs", "tourney_mcts_kwargs"))
+    names = {'<TRAINING_ITERATION>': 7, '<NN_FN>': 'old.h5', '<NEW_NN_FN>': 'new.h5', '<NEURAL_NET>': True}
+
+    def subst(d):
+        return {k: names.get(v, v) if isinstance(v, str) else v for k, v in d.items()}
+    assert TC.default_selfplay_kwargs(7, 'old.h5') == subst(ref["selfplay_kwargs"])
+    assert TC.default_mcts_kwargs(7) == subst(ref["mcts_kwargs"])
+    assert TC.default_mcts_kwargs(0)['NEURAL_NET'] is False               # train_Checkers.py:78
+    assert TC.default_training_kwargs(7) == subst(ref["training_kwargs"])
+    assert TC.default_tourney_kwargs(7, 'old.h5', 'new.h5') == subst(ref["tourney_kwargs"])
+    assert TC.default_tourney_mcts_kwargs('new.h5') == subst(ref["tourney_mcts_kwargs"])
+    play = _dict_literals(os.path.join(H.REFERENCE_DIR, "play_Checkers.py"), ("mcts_kwargs",))["mcts_kwargs"]
+    play.pop('NN_FN')
+    assert P.DEFAULT_MCTS_KWARGS == play
