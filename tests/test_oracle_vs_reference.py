@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import KerasLikeStub, codec
+from helpers import KerasLikeStub, codec, hashed_playouts
 from oracle import oracle as O
 from oracle import ref_harness as H
 
@@ -73,6 +73,39 @@ def test_tree_search_matches_reference_from_midgame():
         got = t.root_children()
         assert [(c["n"], float(c["w"]), float(c["p"])) for c in got] == \
                [(c.n, float(c.w), float(c.p)) for c in root.children]
+
+
+@pytest.mark.parametrize("plies,budget", [(24, 160), (70, 120)])
+def test_uct_playout_search_matches_reference_from_midgame(plies, budget):
+    """NEURAL_NET=False (UCT, one child per visit, a playout per simulation) from positions reached by random play;
+    np.random.randint inside the reference's default_policy is replaced by the position hash the oracle uses"""
+    with H.reference_modules() as ref:
+        env = ref.Checkers.Checkers(None)
+        rng = np.random.RandomState(plies)
+        pos = codec.encode_state(env.state)
+        for _ in range(plies):
+            kids, _, status, _ = O.movegen(pos)
+            if status != 0 or env.done:
+                break
+            i = rng.randint(len(env.legal_next_states))
+            env.step(env.legal_next_states[i])
+            pos = kids[i]
+        assert not env.done
+        ref.MCTS.MCTS(GAME_ENV=env, UCT_C=4, CONSTRAINT='rollout', BUDGET=budget, MULTIPROC=False, NEURAL_NET=False,
+                      VERBOSE=False, TRAINING=False, DIRICHLET_ALPHA=1.0, DIRICHLET_EPSILON=0.0,
+                      TEMPERATURE_TAU=0, TEMPERATURE_DECAY=0, TEMP_DECAY_DELAY=0)
+        root = ref.MCTS.MCTS_Node(env.state)
+        root.history = list(env.history)
+        with hashed_playouts():
+            ref.MCTS.MCTS.begin_tree_search(root)
+        parent_player = int(env.history[-2][4, 0, 0])
+        t = O.Tree(pos, O.make_cfg(budget=budget, rollout="hash"), parent_player=parent_player)
+        t.search(budget)
+        n, w = t.root_stats()
+        assert (n, float(w)) == (root.n, float(root.w))
+        assert [(c["n"], float(c["w"])) for c in t.root_children()] == [(c.n, float(c.w)) for c in root.children]
+        assert [codec.meta_action(c["pos"][3]) for c in t.root_children()] == \
+               [codec.action_id(*[int(v) for v in c.state[14, 0, 0:3]]) for c in root.children]
 
 
 def _dict_literals(path, names):
