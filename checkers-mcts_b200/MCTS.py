@@ -288,7 +288,13 @@ class MCTS_Node(object):
 
     @property
     def unvisited_child_states(self):
-        return [] if (self.children or self.terminal) else MCTS.get_legal_next_states(self.history)
+        """legal successors that are not in the tree yet: all of them before the first visit, none afterwards with
+        a network (all children are added at once), the not yet visited ones with NEURAL_NET=False"""
+        if self.terminal:
+            return []
+        legal = MCTS.get_legal_next_states(self.history)
+        kids = self.children
+        return [s for s in legal if not any((s[:5] == c.state[:5]).all() for c in kids)]
 
     @property
     def w(self):

@@ -166,6 +166,8 @@ def test_iteration0_selfplay_without_network(mods, tmp_path, monkeypatch):
     root = M.MCTS_Node(env.state)
     M.MCTS.begin_tree_search(root)
     assert root.n == 3 and len(root.children) == 3 and len(env.legal_next_states) == 7
+    left = root.unvisited_child_states                          # the reference pops from the end of the legal list
+    assert len(left) == 4 and all((a == b).all() for a, b in zip(left, env.legal_next_states[:4]))
 
 
 def test_train_checkers_iteration_loop(mods, tmp_path, monkeypatch):
