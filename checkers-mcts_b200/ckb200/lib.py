@@ -336,6 +336,8 @@ class Engine(object):
         st = np.zeros(MAX_CHILDREN, dtype=np.int32)
         b = C.c_int32()
         check(_lib.ck_tree_children(self._h, int(node), _ptr(idx), _ptr(pos), _ptr(n), _ptr(w), _ptr(p), _ptr(st), C.byref(b)))
+        if self.cfg.evaluator in (EVAL_ROLLOUT, EVAL_ROLLOUT_HASH):
+            p[:] = 0.0       # no priors without a network (MCTS_Node.p stays 0); the engine keeps its own count in that field
         return [dict(idx=int(idx[i]), pos=tuple(int(v) for v in pos[i]), n=int(n[i]), w=np.float32(w[i]),
                      p=np.float32(p[i]), terminal=int(st[i])) for i in range(b.value)]
 

@@ -216,7 +216,8 @@ int ck_tree_set_root(ck_engine *, const ck_pos *root, int32_t parent_player /* -
 int ck_tree_search(ck_engine *, int32_t sims);
 int ck_tree_root(ck_engine *, uint32_t *n, float *w, int32_t *n_children);
 int ck_tree_root_children(ck_engine *, ck_pos *pos, uint32_t *n, float *w, float *p, int32_t *status);
-/* children of `node` (-1: the root) in node.children order; idx receives their node ids */
+/* children of `node` (-1: the root) in node.children order; idx receives their node ids.  p: the prior
+ * (with the playout evaluators there are no priors and the field holds engine bookkeeping) */
 int ck_tree_children(ck_engine *, int32_t node, int32_t *idx, ck_pos *pos, uint32_t *n, float *w, float *p,
                      int32_t *status, int32_t *count);
 int ck_tree_best_child(ck_engine *, int32_t move_count, int32_t *index);

@@ -329,6 +329,28 @@ def test_uct_first_search_golden_and_midgame_vs_oracle(lib):
     eng.close()
 
 
+def test_wide_node_more_than_32_children_vs_oracle(lib):
+    """a root with 39 legal moves (twelve kings): the second set of child slots of every lane in PUCT / UCT
+    selection, expansion, move selection and the record path -- searches in both modes against the oracle"""
+    pos = (185011974, 1073741824, 1258753798, codec.make_meta(0, 0, 0, 0, 90))
+    assert len(O.movegen(pos)[0]) == 39
+    for evaluator, cfg in (("hash", O.make_cfg(budget=400)), ("rollout_hash", O.make_cfg(budget=400, rollout="hash"))):
+        t = O.Tree(pos, cfg, "hash")
+        eng = lib.Engine(lib.make_cfg(n_slots=1, budget=400, evaluator=evaluator, keep_records=False))
+        eng.tree_set_root(pos)
+        for sims in (20, 400):                                   # 20: the playout mode has added 20 of the 39 children
+            t.search(sims)
+            eng.tree_search(sims)
+            ref = t.root_children()
+            assert eng.tree_root()[:2] == t.root_stats() and eng.tree_root()[2] == len(ref)
+            got = eng.tree_root_children()
+            assert [(c["pos"], c["n"], float(c["w"])) for c in got] == [(c["pos"], c["n"], float(c["w"])) for c in ref]
+            if evaluator == "hash":                              # priors exist with a network only
+                assert [float(c["p"]) for c in got] == [float(c["p"]) for c in ref]
+        assert len(ref) == 39 and eng.tree_best_child() == t.best_child()
+        eng.close()
+
+
 def test_uct_selfplay_game_golden(lib):
     """_generate_data with NEURAL_NET=False run verbatim (hashed playouts): every search of a 40-ply game"""
     gk = json.load(open(os.path.join(GOLDEN, "uct_kat.json")))["game"]
