@@ -21,6 +21,7 @@ EVAL_KINDS = {"net": EVAL_NET, "uniform_zero": EVAL_UNIFORM_ZERO, "uniform_mater
               "hash": EVAL_HASH, "hash_salted": EVAL_HASH_SALTED, "rollout": EVAL_ROLLOUT,
               "rollout_hash": EVAL_ROLLOUT_HASH}
 NET_IMPL_TC, NET_IMPL_SIMT = 0, 1
+ERR_NET_RANGE = 8
 
 from .lib_types import GAME_DTYPE, LEAF_DTYPE, POS_DTYPE, RECORD_DTYPE  # noqa: E402,F401
 
@@ -33,14 +34,15 @@ class EngineCfg(C.Structure):
         ("tau_decay", C.c_double), ("seed", C.c_uint64),
         ("evaluator", C.c_int32), ("evaluator_p2", C.c_int32), ("arena", C.c_int32), ("keep_records", C.c_int32),
         ("reference_tau_quirk", C.c_int32), ("game_id_base", C.c_int32), ("game_id_stride", C.c_int32),
-        ("max_terminal_sims_per_step", C.c_int32), ("compact_always", C.c_int32), ("reserved0", C.c_int32)]
+        ("max_terminal_sims_per_step", C.c_int32), ("compact_always", C.c_int32), ("eval_cache_entries", C.c_int32),
+        ("max_chain_per_step", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class RunStats(C.Structure):
     _fields_ = [("sims", C.c_uint64), ("nn_evals", C.c_uint64), ("steps", C.c_uint64),
                 ("games_finished", C.c_uint64), ("moves", C.c_uint64), ("nodes_created", C.c_uint64),
                 ("compactions", C.c_uint64), ("gpu_ms", C.c_double), ("eval_ms", C.c_double),
-                ("tower_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+                ("tower_ms", C.c_double), ("kernel_launches", C.c_uint64), ("cache_hits", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -75,6 +77,8 @@ def _load():
     L.ck_net_set_weights_device.argtypes = [vp, vp, i64]
     L.ck_net_forward.argtypes = [vp, vp, i64, vp, vp]
     L.ck_net_forward_planes.argtypes = [vp, vp, i64, vp, vp]
+    L.ck_net_forward_logits.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    L.ck_net_range_status.argtypes = [vp]
     L.ck_movegen_csr.argtypes = [C.c_int, vp, i64, vp, i64, vp, vp, vp, vp]
     L.ck_movegen_csr_device.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, vp]
     L.ck_net_forward_device.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -217,6 +221,22 @@ class Net(object):
         check(_lib.ck_net_forward(self._h, _ptr(leaves), n, _ptr(policy), _ptr(value)))
         return policy, value
 
+    def forward_logits(self, leaves):
+        """-> (policy, value, logits [n,512] before the softmax, value before the tanh): the quantities the
+        1e-5 accuracy contract is stated on"""
+        leaves = np.ascontiguousarray(leaves, dtype=LEAF_DTYPE)
+        n = len(leaves)
+        policy = np.empty((n, POLICY_SIZE), dtype=np.float32)
+        value = np.empty(n, dtype=np.float32)
+        logits = np.empty((n, POLICY_SIZE), dtype=np.float32)
+        vpre = np.empty(n, dtype=np.float32)
+        check(_lib.ck_net_forward_logits(self._h, _ptr(leaves), n, _ptr(policy), _ptr(value), _ptr(logits), _ptr(vpre)))
+        return policy, value, logits, vpre
+
+    def range_status(self):
+        """raises CkError(CK_ERR_NET_RANGE) if an activation left the tensor-core path's fp16 range"""
+        check(_lib.ck_net_range_status(self._h))
+
     def predict(self, x):
         """Keras-like predict (Checkers.py:433): x [n,8,8,14] -> [policy [n,512], value [n,1]]."""
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 8, 8, 14)
@@ -242,7 +262,8 @@ class Net(object):
 def make_cfg(n_slots, budget, device=0, uct_c=4.0, training=False, alpha=1.0, epsilon=0.0, tau=0.0,
              tau_decay=0.0, tau_decay_delay=0, terminate_cnt=0, seed=1, evaluator="net", evaluator_p2=None,
              arena=False, keep_records=True, pool_cap=0, max_plies=0, reference_tau_quirk=False,
-             game_id_base=0, game_id_stride=1, max_terminal_sims_per_step=0, compact_always=False):
+             game_id_base=0, game_id_stride=1, max_terminal_sims_per_step=0, compact_always=False,
+             eval_cache_entries=0, max_chain_per_step=0):
     ev = EVAL_KINDS[evaluator] if isinstance(evaluator, str) else int(evaluator)
     ev2 = -1 if evaluator_p2 is None else (EVAL_KINDS[evaluator_p2] if isinstance(evaluator_p2, str) else int(evaluator_p2))
     return EngineCfg(device=device, n_slots=n_slots, pool_cap=pool_cap, max_plies=max_plies, budget=budget,
@@ -251,7 +272,8 @@ def make_cfg(n_slots, budget, device=0, uct_c=4.0, training=False, alpha=1.0, ep
                      evaluator=ev, evaluator_p2=ev2, arena=int(bool(arena)), keep_records=int(bool(keep_records)),
                      reference_tau_quirk=int(bool(reference_tau_quirk)), game_id_base=game_id_base,
                      game_id_stride=game_id_stride, max_terminal_sims_per_step=max_terminal_sims_per_step,
-                     compact_always=int(bool(compact_always)), reserved0=0)
+                     compact_always=int(bool(compact_always)), eval_cache_entries=int(eval_cache_entries),
+                     max_chain_per_step=int(max_chain_per_step), reserved0=0)
 
 
 class Engine(object):

@@ -50,6 +50,7 @@ struct Slot {
     double tau;
     unsigned long long tot_sims, tot_evals;      // monotonic per slot; per-game totals are deltas
     unsigned long long g_sims0, g_evals0;
+    unsigned long long tot_hits;                 // expansions served by the evaluation cache (a subset of tot_evals)
 };
 
 struct Counters {
@@ -75,6 +76,10 @@ struct EngineDev {
     const double *log_tab;       // host libm log(n) table (np.log(node.n), MCTS.py:114); rollout evaluators only
     int32_t uct;                 // 1: NEURAL_NET=False tree policy (UCT, one child per visit, playouts)
     uint32_t round;              // lock-step round counter (keys the random playouts)
+    uint4 *cache;                // evaluation cache [slot][cache_entries][8 x uint4]; nullptr: off
+    int32_t cache_entries;       // per slot, a power of two
+    int32_t max_chain;           // simulations a slot may complete inside one round without a network evaluation (terminal + cached)
+    int32_t cache_game_tag;      // 1: the evaluator depends on the game (salted stubs), so entries are tagged with it
 };
 
 // ---- small device helpers --------------------------------------------------------------
@@ -255,6 +260,7 @@ __device__ int select_leaf(const WarpCtx &c, int *out_depth) {
             const bool take = (oi != kNoIdx) && (best_i == kNoIdx || ou > best_u || (ou == best_u && oi < best_i));
             if (take) { best_u = ou; best_i = oi; }
         }
+        best_i = __shfl_sync(CK_FULL, best_i, 0);       // lanes agree by construction unless scores are NaN (a network out of range): stay converged
         const uint4 pick = best_i < 32 ? shfl4(c0, best_i) : shfl4(c1, best_i - 32);
         node = fc + best_i;
         ++depth;
@@ -291,13 +297,39 @@ __device__ void stage_leaf(const WarpCtx &c, int leaf, int depth) {
     __syncwarp();
 }
 
-// Expansion of the evaluated leaf (MCTS.py:71-77): all children at once in reversed legal
-// order, each with its own terminal test (MCTS_Node.__init__, :374-375), priors from the
-// masked + renormalised policy (Checkers.py:434-452), then the signed value backup.
-__device__ void expand_pending(const WarpCtx &c) {
+// ---- evaluation cache ---------------------------------------------------------------------------
+// Half of a game's leaf evaluations repeat an earlier evaluation of the same network input: each colour
+// searches its own tree (training_pipeline.py:353,372) over nearly the same positions, and a tree holds
+// transpositions as separate nodes (scripts/dup_rate.py: 46-50 % of the evaluations of a cfg2 game, median
+// distance 150-230 evaluations).  The network is a pure function of (position, side to move, plane 5) --
+// the legal-action planes follow from the position -- so what an expansion needs from it, the children's
+// priors (Checkers.predict's masked, renormalised policy, Checkers.py:434-452) and the value, is kept in a
+// direct-mapped table per slot: 128 B per entry = key (p1, p2, k, tag) | value | up to 24 priors in
+// node.children order.  A hit expands the leaf inside the same round with bit-identical numbers; results do
+// not depend on the cache (tests run with and without it).  One warp owns a slot, so there are no races.
+constexpr int kCachePriors = 24;
+constexpr int kCacheU4 = 8;                          // uint4 per entry
+__device__ __forceinline__ int p5_ongoing(uint32_t meta) {      // plane-5 numerator of a position that is not a draw (outcome_of)
+    return meta_ply(meta) + 1 >= 80 ? meta_rev(meta) + 1 : 0;
+}
+__device__ __forceinline__ uint32_t cache_tag(const EngineDev &E, const Slot &S, uint32_t meta, int net) {
+    return 0x80000000u | (meta & 1u) | ((uint32_t)p5_ongoing(meta) << 1) | ((uint32_t)net << 8) |
+           (E.cache_game_tag ? (((uint32_t)S.game & 0x3FFFFFu) << 9) : 0u);
+}
+__device__ __forceinline__ uint4 *cache_entry(const WarpCtx &c, const ck_pos &p, uint32_t tag) {
+    const uint32_t h = mix32(p.p1 * 0x9E3779B1u ^ mix32(p.p2 ^ mix32(p.k + tag * 0x85EBCA6Bu)));
+    return c.E.cache + ((int64_t)c.slot * c.E.cache_entries + (int64_t)(h & (uint32_t)(c.E.cache_entries - 1))) * kCacheU4;
+}
+
+// Expansion of a leaf (MCTS.py:71-77): all children at once in reversed legal order, each with its
+// own terminal test (MCTS_Node.__init__, :374-375), priors from the masked + renormalised policy
+// (Checkers.py:434-452), then the signed value backup.  kHit: priors and value come from the slot's
+// evaluation cache (`entry`), otherwise from the evaluator's output row, and the entry is (re)written.
+template <bool kHit>
+__device__ void expand_leaf(const WarpCtx &c, int leaf, int depth, int net, int row, uint4 *entry, uint32_t tag) {
     const EngineDev &E = c.E;
     Slot &S = c.S;
-    const int t = S.cur, leaf = S.pend_leaf, net = S.pend_net;
+    const int t = S.cur;
     uint4 *pos = c.pos_of(t), *stat = c.stat_of(t);
     const ck_pos lp = to_pos(pos[leaf]);
     // every lane derives the legal-action planes itself (a few dozen bit operations); the successors are
@@ -309,10 +341,16 @@ __device__ void expand_pending(const WarpCtx &c) {
     const Side lsd = side_of(lp);
     uint32_t hop[4];
     hop_sets(lsd, hop);
-    const float *prow = E.policy[net] + (int64_t)S.pend_row * CK_POLICY_SIZE;
-    float masked[16];
-    const float psum = masked_policy_sum(prow, mask, c.lane, masked);
-    const float value = E.value[net][S.pend_row];
+    const float *prow = nullptr;
+    float psum = 1.f, value;
+    if (kHit) {
+        value = __uint_as_float(entry[1].x);
+    } else {
+        prow = E.policy[net] + (int64_t)row * CK_POLICY_SIZE;
+        float masked[16];
+        psum = masked_policy_sum(prow, mask, c.lane, masked);
+        value = E.value[net][row];
+    }
     const int fc = S.alloc[t];
     if (fc + b > E.cap) {
         dev_error(E, CK_ERR_POOL_OVERFLOW);
@@ -320,6 +358,8 @@ __device__ void expand_pending(const WarpCtx &c) {
         __syncwarp();
         return;
     }
+    const bool fill = !kHit && entry != nullptr && b <= kCachePriors;
+    float *eprior = entry ? reinterpret_cast<float *>(entry + 2) : nullptr;
     const int lplayer = meta_player(lp.meta);
     for (int i = c.lane; i < b; i += 32) {
         int ms, md;
@@ -327,7 +367,8 @@ __device__ void expand_pending(const WarpCtx &c) {
         const ck_pos ch = make_child_fast(lp, lsd, hop, ms, md, jump);
         int p5;
         const int stc = status_of(ch, &p5);
-        const float prior = __fdiv_rn(prow[meta_action(ch.meta)], psum);
+        const float prior = kHit ? eprior[i] : __fdiv_rn(prow[meta_action(ch.meta)], psum);
+        if (fill) eprior[i] = prior;
         pos[fc + i] = from_pos(ch);
         stat[fc + i] = make_uint4(0u, __float_as_uint(0.f), __float_as_uint(prior),
                                   ((uint32_t)stc << 28) | ((uint32_t)lplayer << 30));
@@ -339,10 +380,41 @@ __device__ void expand_pending(const WarpCtx &c) {
         S.alloc[t] = fc + b;
         S.pend_leaf = -1;
         S.tot_evals += 1; S.tot_sims += 1; S.sims_done += 1;
+        if (kHit) S.tot_hits += 1;
+        if (fill) {
+            entry[1] = make_uint4(__float_as_uint(value), (uint32_t)b, 0u, 0u);
+            entry[0] = make_uint4(lp.p1, lp.p2, lp.k, tag);
+        }
         atomicAdd(&E.ctr->nodes, (unsigned long long)b);
     }
     __syncwarp();
-    backup(c, S.pend_depth, false, 0, value, lplayer);
+    backup(c, depth, false, 0, value, lplayer);
+}
+
+// the evaluation the previous round staged has arrived
+__device__ void expand_pending(const WarpCtx &c) {
+    Slot &S = c.S;
+    uint4 *entry = nullptr;
+    uint32_t tag = 0u;
+    if (c.E.cache) {
+        const ck_pos lp = to_pos(c.pos_of(S.cur)[S.pend_leaf]);
+        tag = cache_tag(c.E, S, lp.meta, S.pend_net);
+        entry = cache_entry(c, lp, tag);
+    }
+    expand_leaf<false>(c, S.pend_leaf, S.pend_depth, S.pend_net, S.pend_row, entry, tag);
+}
+
+// leaf found by the descent: expand it from the cache if its input was evaluated before
+__device__ bool expand_cached(const WarpCtx &c, int leaf, int depth) {
+    const Slot &S = c.S;
+    const ck_pos lp = to_pos(c.pos_of(S.cur)[leaf]);
+    const int net = net_of(c.E, S.game, S.cur);
+    const uint32_t tag = cache_tag(c.E, S, lp.meta, net);
+    uint4 *entry = cache_entry(c, lp, tag);
+    const uint4 key = entry[0];
+    if (key.x != lp.p1 || key.y != lp.p2 || key.z != lp.k || key.w != tag) return false;
+    expand_leaf<true>(c, leaf, depth, net, 0, entry, tag);
+    return true;
 }
 
 // ---- NEURAL_NET=False (the reference's iteration-0 self-play, MCTS.py:78-89,113-115,132-146) ---------
@@ -460,8 +532,9 @@ __device__ void stage_playout(const WarpCtx &c, int leaf, int depth) {
         L.p1 = p.p1; L.p2 = p.p2; L.k = p.k;
         L.info = (p.meta & 1u) | (((uint32_t)global_game(E, S.game) & 0xFFFFu) << 16);
         L.mask[0] = p.meta;
+        L.mask[1] = (uint32_t)global_game(E, S.game);    // the full game id keys the playout's random stream
 #pragma unroll
-        for (int i = 1; i < 8; ++i) L.mask[i] = 0u;
+        for (int i = 2; i < 8; ++i) L.mask[i] = 0u;
         const int row = atomicAdd(&E.ctr->batch_count[0], 1);
         E.leaves[0][row] = L;
         S.pend_leaf = leaf; S.pend_row = row; S.pend_depth = depth; S.pend_net = 0;
@@ -793,8 +866,8 @@ tree_step_kernel(const EngineDev E) {
     if (live && S.game < 0) live = S.manual ? false : refill(c);
     if (live && S.phase == PH_HALT) live = false;
     if (live && S.pend_leaf >= 0) { if (kUct) finish_playout(c); else expand_pending(c); }
-    int term_iters = 0;
-    const int max_term = E.max_term;
+    int term_iters = 0, chain = 0;
+    const int max_term = E.max_term, max_chain = E.max_chain;
     while (live && S.phase != PH_HALT) {
         if (S.phase == PH_NEED_ROOT) setup_root(c);
         const int target = S.manual ? S.manual_target : E.cfg.budget;
@@ -805,12 +878,20 @@ tree_step_kernel(const EngineDev E) {
         }
         int depth = 0;
         const int leaf = kUct ? select_leaf_uct(c, &depth) : select_leaf(c, &depth);
-        if (leaf >= 0) { if (kUct) stage_playout(c, leaf, depth); else stage_leaf(c, leaf, depth); break; }
+        if (leaf >= 0) {
+            if (kUct) { stage_playout(c, leaf, depth); break; }
+            if (E.cache != nullptr && expand_cached(c, leaf, depth)) {       // evaluated before: no network call
+                if (S.phase == PH_HALT || ++chain >= max_chain) break;
+                continue;
+            }
+            stage_leaf(c, leaf, depth);
+            break;
+        }
         __syncwarp();
         if (leaf == -2) { if (lane == 0) S.phase = PH_HALT; __syncwarp(); break; }
         if (lane == 0) { S.tot_sims += 1; S.sims_done += 1; }
         __syncwarp();
-        if (++term_iters >= max_term) break;
+        if (++term_iters >= max_term || ++chain >= max_chain) break;
     }
     if (lane == 0 && S.game >= 0 && S.phase != PH_HALT) atomicAdd(&E.ctr->active, 1);
     __syncwarp();
@@ -841,12 +922,12 @@ __global__ void __launch_bounds__(32) manual_compact_kernel(const EngineDev E) {
 }
 
 // simulation / evaluation totals live per slot (no hot-path atomics); summed on demand
-__global__ void sum_slots_kernel(const EngineDev E, unsigned long long *out_sims, unsigned long long *out_evals) {
-    unsigned long long s = 0, e = 0;
+__global__ void sum_slots_kernel(const EngineDev E, unsigned long long *out /* sims, evals, cache hits */) {
+    unsigned long long s = 0, e = 0, h = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E.n_slots; i += gridDim.x * blockDim.x) {
-        s += E.slots[i].tot_sims; e += E.slots[i].tot_evals;
+        s += E.slots[i].tot_sims; e += E.slots[i].tot_evals; h += E.slots[i].tot_hits;
     }
-    atomicAdd(out_sims, s); atomicAdd(out_evals, e);
+    atomicAdd(out, s); atomicAdd(out + 1, e); atomicAdd(out + 2, h);
 }
 
 // ---- stub evaluators (deterministic parity tests; twins of the oracle's cko_eval_*) ----------
@@ -906,9 +987,9 @@ playout_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restric
     cur.p1 = L.p1; cur.p2 = L.p2; cur.k = L.k; cur.meta = L.mask[0];
     int st;
     if (kind == CK_EVAL_ROLLOUT_HASH) {
-        st = play_out(cur, 0, HashChoice{L.info >> 16}, nullptr);            // salted with the game tag
+        st = play_out(cur, 0, HashChoice{L.mask[1]}, nullptr);               // salted with the game id
     } else {
-        st = play_out(cur, 0, PhiloxChoice{Philox(mix64(seed ^ mix64(((uint64_t)(L.info >> 16) << 32) | round))), 0x504C4159u}, nullptr);
+        st = play_out(cur, 0, PhiloxChoice{Philox(mix64(seed ^ mix64(((uint64_t)L.mask[1] << 32) | round))), 0x504C4159u}, nullptr);
     }
     value[row] = (float)st;
 }
@@ -923,6 +1004,7 @@ using namespace ck;
 struct ck_engine {
     EngineDev dev;           // device pointers + config, passed by value to the kernels
     ck_net *net[2] = {nullptr, nullptr};
+    uint64_t net_gen[2] = {0, 0};       // weights generation the evaluation cache was filled under
     cudaStream_t stream = nullptr;
     cudaStream_t stream_b = nullptr;    // arena: the second network evaluates next to the first one
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
@@ -944,6 +1026,7 @@ static void engine_free(ck_engine *e) {
     cudaFree(d.pos); cudaFree(d.stat); cudaFree(d.hist); cudaFree(d.path); cudaFree(d.slots); cudaFree(d.ctr);
     for (int k = 0; k < 2; ++k) { cudaFree(d.leaves[k]); cudaFree(d.policy[k]); cudaFree(d.value[k]); }
     cudaFree(d.rec); cudaFree(d.results); cudaFree((void *)d.pow_half); cudaFree((void *)d.log_tab); cudaFree(e->d_tot);
+    cudaFree(d.cache);
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->stream_b) cudaStreamDestroy(e->stream_b);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -1005,6 +1088,17 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     // per round the steady-state tree_step took 0.35 ms instead of 0.1 ms: scripts/long_run.py), so the
     // default lets a slot finish four and carries the rest into the next rounds.
     d.max_term = cfg->max_terminal_sims_per_step > 0 ? cfg->max_terminal_sims_per_step : 4;
+    d.max_chain = cfg->max_chain_per_step > 0 ? cfg->max_chain_per_step : 8;
+    if (d.max_chain < d.max_term) d.max_chain = d.max_term;
+    // evaluation cache: per slot a power of two of 128-byte entries (default 4096 = 512 KB per slot); the playout
+    // modes have no network, the uniform stubs nothing worth caching (but they exercise the path in the tests)
+    if (!uct && cfg->eval_cache_entries >= 0) {
+        int want = cfg->eval_cache_entries > 0 ? cfg->eval_cache_entries : 4096;
+        int ent = 16;
+        while (ent < want && ent < (1 << 20)) ent *= 2;
+        d.cache_entries = ent;
+        d.cache_game_tag = (cfg->evaluator == CK_EVAL_HASH_SALTED || cfg->evaluator_p2 == CK_EVAL_HASH_SALTED) ? 1 : 0;
+    }
     d.one_minus_eps = (float)(1.0 - cfg->epsilon);       // (1 - eps) * float32 array stays float32 (numpy >= 2)
     if (cfg->keep_records) d.max_rec = (cfg->terminate_cnt > 0 ? cfg->terminate_cnt : d.max_plies) + 1;
     CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -1027,8 +1121,13 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         CK_E(cudaMalloc(&d.policy[k], (size_t)d.n_slots * CK_POLICY_SIZE * sizeof(float)));
         CK_E(cudaMalloc(&d.value[k], (size_t)d.n_slots * sizeof(float)));
     }
-    CK_E(cudaMallocHost(&e->h_ctr, sizeof(Counters)));
-    CK_E(cudaMalloc(&e->d_tot, 4 * sizeof(unsigned long long)));
+    if (d.cache_entries > 0) {
+        const size_t bytes = (size_t)d.n_slots * d.cache_entries * kCacheU4 * sizeof(uint4);
+        CK_E(cudaMalloc(&d.cache, bytes));
+        CK_E(cudaMemset(d.cache, 0, bytes));
+    }
+    CK_E(cudaMallocHost(&e->h_ctr, sizeof(Counters) + 2 * sizeof(int32_t)));   // + the two networks' range flags
+    CK_E(cudaMalloc(&e->d_tot, 6 * sizeof(unsigned long long)));
     {
         // node.n ** 0.5 is libm pow in the reference (MCTS.py:110) and differs from sqrt for
         // some integers; the table is built with the host's libm so the two agree.
@@ -1070,12 +1169,24 @@ int ck_engine_set_net(ck_engine *e, int which, ck_net *net) {
     if (!e || which < 0 || which > 1 || !net) return fail(CK_ERR_ARG, "ck_engine_set_net: bad arguments");
     if (net->device != e->dev.cfg.device) return fail(CK_ERR_ARG, "ck_engine_set_net: net lives on another device");
     e->net[which] = net;
+    e->net_gen[which] = 0;              // (generations start at 1) the next run clears the evaluation cache
     return CK_OK;
 }
 
 int ck_engine_set_profile(ck_engine *e, int on) {
     if (!e) return fail(CK_ERR_ARG, "ck_engine_set_profile: null engine");
     e->profile = on != 0;
+    return CK_OK;
+}
+
+// cached evaluations are only valid for the weights they were computed with
+static int engine_check_cache(ck_engine *e) {
+    EngineDev &d = e->dev;
+    if (!d.cache || d.cfg.evaluator != CK_EVAL_NET) return CK_OK;
+    bool stale = false;
+    for (int k = 0; k < 2; ++k)
+        if (e->net[k] && e->net[k]->weights_gen != e->net_gen[k]) { stale = true; e->net_gen[k] = e->net[k]->weights_gen; }
+    if (stale) CK_CUDA(cudaMemsetAsync(d.cache, 0, (size_t)d.n_slots * d.cache_entries * kCacheU4 * sizeof(uint4), e->stream));
     return CK_OK;
 }
 
@@ -1183,7 +1294,17 @@ static int engine_round(ck_engine *e, int *launches) {
 
 static int engine_poll(ck_engine *e) {
     CK_CUDA(cudaMemcpyAsync(e->h_ctr, e->dev.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+    int32_t *h_range = reinterpret_cast<int32_t *>(e->h_ctr + 1);
+    h_range[0] = h_range[1] = 0;
+    if (e->dev.cfg.evaluator == CK_EVAL_NET)
+        for (int k = 0; k < 2; ++k)
+            if (e->net[k]) CK_CUDA(cudaMemcpyAsync(h_range + k, e->net[k]->d_range_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK_CUDA(cudaStreamSynchronize(e->stream));
+    if (h_range[0] | h_range[1]) {
+        for (int k = 0; k < 2; ++k) if (e->net[k]) cudaMemsetAsync(e->net[k]->d_range_flag, 0, sizeof(int32_t), e->stream);
+        return fail(CK_ERR_NET_RANGE, "engine: a network activation left the split-fp16 range of the tensor-core evaluator "
+                                      "(searches since the last check used invalid priors); use CK_NET_IMPL_SIMT for these weights");
+    }
     if (e->h_ctr->error != 0) {
         const int code = e->h_ctr->error;
         return fail(code, code == CK_ERR_POOL_OVERFLOW ? "engine: node pool overflow (raise pool_cap)" :
@@ -1196,12 +1317,14 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
     if (!e || !e->begun) return fail(CK_ERR_STATE, "ck_engine_run: call ck_engine_begin first");
     EngineDev &d = e->dev;
     DeviceGuard g(d.cfg.device);
-    int rc = engine_poll(e);
+    int rc = engine_check_cache(e);
+    if (rc != CK_OK) return rc;
+    rc = engine_poll(e);
     if (rc != CK_OK) return rc;
     const Counters before = *e->h_ctr;
     unsigned long long *d_tot = e->d_tot;
-    CK_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), e->stream));
-    sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot, d_tot + 1);
+    CK_CUDA(cudaMemsetAsync(d_tot, 0, 6 * sizeof(unsigned long long), e->stream));
+    sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot);
     int launches = 0;
     double eval_ms = 0.0, tower_ms = 0.0;
     CK_CUDA(cudaEventRecord(e->ev0, e->stream));
@@ -1245,8 +1368,8 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         if (n_steps <= 0 && e->h_ctr->games_finished >= (unsigned long long)e->n_games) break;
     }
     CK_CUDA(cudaEventRecord(e->ev1, e->stream));
-    sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot + 2, d_tot + 3);
-    unsigned long long tot[4];
+    sum_slots_kernel<<<32, 128, 0, e->stream>>>(d, d_tot + 3);
+    unsigned long long tot[6];
     CK_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, e->stream));
     CK_CUDA(cudaStreamSynchronize(e->stream));
     e->total_steps += (uint64_t)steps;
@@ -1264,7 +1387,7 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         stats->eval_ms = eval_ms;
         stats->tower_ms = tower_ms;
         stats->kernel_launches = (uint64_t)launches;
-        stats->sims = tot[2] - tot[0]; stats->nn_evals = tot[3] - tot[1];
+        stats->sims = tot[3] - tot[0]; stats->nn_evals = tot[4] - tot[1]; stats->cache_hits = tot[5] - tot[2];
     }
     return CK_OK;
 }
@@ -1405,6 +1528,8 @@ int ck_tree_search(ck_engine *e, int32_t sims) {
     DeviceGuard g(d.cfg.device);
     Slot s;
     int rc = manual_slot(e, &s);
+    if (rc != CK_OK) return rc;
+    rc = engine_check_cache(e);
     if (rc != CK_OK) return rc;
     s.manual_target = sims; s.sims_done = 0;       // BUDGET new simulations on top of inherited statistics (MCTS.py:217)
     s.search_id += 1;                              // a new search draws new exploration noise

@@ -36,7 +36,7 @@ constexpr uint32_t kIdesc = make_idesc_f16(kM, kN);
 __global__ void __launch_bounds__(kThreads, 1)
 heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int32_t *__restrict__ n_dev,
                       const uint8_t *__restrict__ wpack, const float *__restrict__ bias, const float *__restrict__ inv_scale,
-                      float *__restrict__ logits) {
+                      float *__restrict__ logits, int32_t *__restrict__ range_flag) {
     extern __shared__ __align__(1024) uint8_t smem[];
     int64_t n = max_n;
     if (n_dev != nullptr) n = min((int64_t)*n_dev, max_n);
@@ -77,12 +77,15 @@ heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int3
                 for (int e = 0; e < 8; ++e) v[e] = 0.f;
             }
             __half hi[8], lo[8];
+            bool bad = false;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float s = v[e] * kActScale;
+                bad |= !(fabsf(s) < 65504.f);
                 hi[e] = __float2half_rn(s);
                 lo[e] = __float2half_rn(s - __half2float(hi[e]));
             }
+            if (bad) atomicExch(range_flag, 1);                     // beyond fp16 (or NaN from the tower): never silent
             uint8_t *dst = s_a + u * (kM * 16) + m * 16;
             *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
             *reinterpret_cast<uint4 *>(dst + kSplit) = *reinterpret_cast<const uint4 *>(lo);
@@ -141,7 +144,7 @@ struct FinishParams { int64_t val_d1_k, val_d1_b, val_d2_k, val_d2_b; };
 __global__ void __launch_bounds__(256)
 heads_finish_kernel(const float *__restrict__ logits, const float *__restrict__ vconv, int64_t max_n,
                     const int32_t *__restrict__ n_dev, const float *__restrict__ blob, const float *__restrict__ fold,
-                    FinishParams hp, float *__restrict__ policy, float *__restrict__ value) {
+                    FinishParams hp, float *__restrict__ policy, float *__restrict__ value, float *__restrict__ value_pre) {
     int64_t n = max_n;
     if (n_dev != nullptr) n = min((int64_t)*n_dev, max_n);
     const int lane = threadIdx.x & 31;
@@ -176,7 +179,10 @@ heads_finish_kernel(const float *__restrict__ logits, const float *__restrict__ 
     float t = h0 * blob[hp.val_d2_k + lane] + h1 * blob[hp.val_d2_k + 32 + lane];
 #pragma unroll
     for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
-    if (lane == 0) value[p] = tanhf(t + blob[hp.val_d2_b]);
+    if (lane == 0) {
+        value[p] = tanhf(t + blob[hp.val_d2_b]);
+        if (value_pre != nullptr) value_pre[p] = t + blob[hp.val_d2_b];
+    }
 }
 
 // ---- weight packing ----------------------------------------------------------------------------
@@ -238,10 +244,10 @@ int net_heads_tc(ck_net *net, const float *d_pflat, const float *d_vconv, float 
     const float *aux = (const float *)((const uint8_t *)net->d_hpack + htc::kPackBytes);
     const dim3 grid((unsigned)((max_n + htc::kM - 1) / htc::kM), 4);
     htc::heads_dense_tc_kernel<<<grid, htc::kThreads, htc::kSmem, stream>>>(
-        d_pflat, max_n, n_dev, (const uint8_t *)net->d_hpack, net->d_blob + L.pol_dense_b, aux, d_logits);
+        d_pflat, max_n, n_dev, (const uint8_t *)net->d_hpack, net->d_blob + L.pol_dense_b, aux, d_logits, net->d_range_flag);
     htc::FinishParams hp{L.val_d1_k, L.val_d1_b, L.val_d2_k, L.val_d2_b};
     htc::heads_finish_kernel<<<(unsigned)((max_n + 7) / 8), 256, 0, stream>>>(
-        d_logits, d_vconv, max_n, n_dev, net->d_blob, net->d_scale, hp, d_policy, d_value);
+        d_logits, d_vconv, max_n, n_dev, net->d_blob, net->d_scale, hp, d_policy, d_value, net->d_value_pre);
     CK_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
     return CK_OK;

@@ -188,7 +188,8 @@ template <bool kFused>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, int64_t max_n,
              const int32_t *__restrict__ n_dev, const float *__restrict__ blob, const float *__restrict__ fold,
-             HeadParams hp, float *__restrict__ policy, float *__restrict__ value) {
+             HeadParams hp, float *__restrict__ policy, float *__restrict__ value,
+             float *__restrict__ logits_out, float *__restrict__ vpre_out) {
     int64_t n = max_n;
     if (n_dev != nullptr) n = min((int64_t)*n_dev, max_n);
     const int64_t base = (int64_t)blockIdx.x * kHeadPB;
@@ -281,6 +282,8 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
 #pragma unroll
         for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
         float e[16], s = 0.f;
+        if (logits_out != nullptr)
+            for (int i = lane; i < 512; i += 32) logits_out[(base + p) * 512 + i] = row[i];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { e[i] = expf(row[lane + 32 * i] - m); s += e[i]; }
 #pragma unroll
@@ -300,7 +303,10 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
         float t = h0 * blob[hp.val_d2_k + lane] + h1 * blob[hp.val_d2_k + 32 + lane];
 #pragma unroll
         for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
-        if (lane == 0) value[base + p] = tanhf(t + blob[hp.val_d2_b]);
+        if (lane == 0) {
+            value[base + p] = tanhf(t + blob[hp.val_d2_b]);
+            if (vpre_out != nullptr) vpre_out[base + p] = t + blob[hp.val_d2_b];
+        }
     }
 }
 
@@ -347,6 +353,7 @@ static int net_finish_weights(ck_net *net) {
     if (rc != CK_OK) return rc;
     CK_CUDA(cudaDeviceSynchronize());
     net->have_weights = true;
+    net->weights_gen += 1;
     return CK_OK;
 }
 
@@ -408,16 +415,29 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
         // d_act1 = [pflat n x 512 | logits n x 512 | ...], d_act0 = vconv
         rc = net_heads_tc(net, pconv, trunk, pconv + max_n * 512, max_n, n_dev, d_policy, d_value, stream, &nl);
         if (rc != CK_OK) return rc;
+        if (net->d_logits_out)
+            CK_CUDA(cudaMemcpyAsync(net->d_logits_out, pconv + max_n * 512, (size_t)max_n * 512 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     } else if (fused) {
-        heads_kernel<true><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
+        heads_kernel<true><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value,
+                                                                       net->d_logits_out, net->d_value_pre);
         ++nl;
     } else {
-        heads_kernel<false><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value);
+        heads_kernel<false><<<hgrid, kHeadThreads, kHeadSmem, stream>>>(trunk, pconv, max_n, n_dev, blob, net->d_scale, hp, d_policy, d_value,
+                                                                        net->d_logits_out, net->d_value_pre);
         ++nl;
     }
     CK_CUDA(cudaGetLastError());
     if (launches) *launches += nl;
     return CK_OK;
+}
+
+int net_check_range(ck_net *net) {
+    int32_t flag = 0;
+    CK_CUDA(cudaMemcpy(&flag, net->d_range_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag == 0) return CK_OK;
+    CK_CUDA(cudaMemset(net->d_range_flag, 0, sizeof(flag)));
+    return fail(CK_ERR_NET_RANGE, "network activation beyond the split-fp16 range of the tensor-core path (|a| >= 4094 after a "
+                                  "BatchNorm, or non-finite): outputs of this call are invalid; use CK_NET_IMPL_SIMT for these weights");
 }
 
 }  // namespace ck
@@ -432,6 +452,8 @@ ck_net *ck_net_create(int device) {
     ck_net *net = new ck_net();
     net->device = device;
     CK_CUDA_PTR(cudaMalloc(&net->d_blob, CK_NET_PARAM_COUNT * sizeof(float)));
+    CK_CUDA_PTR(cudaMalloc(&net->d_range_flag, sizeof(int32_t)));
+    CK_CUDA_PTR(cudaMemset(net->d_range_flag, 0, sizeof(int32_t)));
     return net;
 }
 
@@ -440,7 +462,7 @@ void ck_net_destroy(ck_net *net) {
     DeviceGuard g(net->device);
     cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack); cudaFree(net->d_wts); cudaFree(net->d_hpack);
     cudaFree(net->d_act0); cudaFree(net->d_act1);
-    cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value);
+    cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value); cudaFree(net->d_range_flag);
     delete net;
 }
 
@@ -482,9 +504,44 @@ int ck_net_forward(ck_net *net, const ck_leaf *leaves, int64_t n, float *policy,
     rc = net_forward_rows(net, net->d_leaves, n, nullptr, net->d_policy, net->d_value, nullptr, nullptr);
     if (rc != CK_OK) return rc;
     CK_CUDA(cudaDeviceSynchronize());
+    rc = net_check_range(net);
+    if (rc != CK_OK) return rc;
     if (policy) CK_CUDA(cudaMemcpy(policy, net->d_policy, n * CK_POLICY_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
     if (value) CK_CUDA(cudaMemcpy(value, net->d_value, n * sizeof(float), cudaMemcpyDeviceToHost));
     return CK_OK;
+}
+
+int ck_net_forward_logits(ck_net *net, const ck_leaf *leaves, int64_t n, float *policy, float *value, float *logits, float *value_pre) {
+    if (!net || !leaves || n < 0) return fail(CK_ERR_ARG, "ck_net_forward_logits: bad arguments");
+    if (n == 0) return CK_OK;
+    DeviceGuard g(net->device);
+    int rc = net_reserve_io(net, n);
+    if (rc != CK_OK) return rc;
+    float *d_dbg = nullptr;                                   // [n][512] logits + [n] pre-tanh values
+    CK_CUDA(cudaMalloc(&d_dbg, (size_t)n * 513 * sizeof(float)));
+    net->d_logits_out = d_dbg; net->d_value_pre = d_dbg + n * 512;
+    cudaError_t ce = cudaMemcpy(net->d_leaves, leaves, n * sizeof(ck_leaf), cudaMemcpyHostToDevice);
+    rc = ce == cudaSuccess ? net_forward_rows(net, net->d_leaves, n, nullptr, net->d_policy, net->d_value, nullptr, nullptr) : CK_ERR_CUDA;
+    net->d_logits_out = nullptr; net->d_value_pre = nullptr;
+    if (rc == CK_OK && cudaDeviceSynchronize() != cudaSuccess) rc = CK_ERR_CUDA;
+    if (rc == CK_OK) rc = net_check_range(net);
+    if (rc == CK_OK) {
+        if (policy) ce = cudaMemcpy(policy, net->d_policy, n * CK_POLICY_SIZE * sizeof(float), cudaMemcpyDeviceToHost);
+        if (value && ce == cudaSuccess) ce = cudaMemcpy(value, net->d_value, n * sizeof(float), cudaMemcpyDeviceToHost);
+        if (logits && ce == cudaSuccess) ce = cudaMemcpy(logits, d_dbg, (size_t)n * 512 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (value_pre && ce == cudaSuccess) ce = cudaMemcpy(value_pre, d_dbg + n * 512, n * sizeof(float), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) rc = CK_ERR_CUDA;
+    }
+    cudaFree(d_dbg);
+    if (rc == CK_ERR_CUDA && ce != cudaSuccess) return fail(CK_ERR_CUDA, std::string("ck_net_forward_logits: ") + cudaGetErrorString(ce));
+    return rc;
+}
+
+int ck_net_range_status(ck_net *net) {
+    if (!net) return fail(CK_ERR_ARG, "ck_net_range_status: null net");
+    DeviceGuard g(net->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(CK_ERR_CUDA, "ck_net_range_status: device error");
+    return net_check_range(net);
 }
 
 int ck_net_forward_planes(ck_net *net, const float *x, int64_t n, float *policy, float *value) {
@@ -505,6 +562,8 @@ int ck_net_forward_planes(ck_net *net, const float *x, int64_t n, float *policy,
     rc = net_forward_rows(net, net->d_leaves, n, nullptr, net->d_policy, net->d_value, nullptr, nullptr);
     if (rc != CK_OK) return rc;
     CK_CUDA(cudaDeviceSynchronize());
+    rc = net_check_range(net);
+    if (rc != CK_OK) return rc;
     if (policy) CK_CUDA(cudaMemcpy(policy, net->d_policy, n * CK_POLICY_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
     if (value) CK_CUDA(cudaMemcpy(value, net->d_value, n * sizeof(float), cudaMemcpyDeviceToHost));
     return CK_OK;

@@ -27,6 +27,7 @@ struct ck_net {
     int device = 0;
     int impl = CK_NET_IMPL_TC;
     bool have_weights = false;
+    uint64_t weights_gen = 0;        // bumped by every ck_net_set_weights*: consumers that cache evaluations compare it
     float *d_blob = nullptr;         // Keras-ordered fp32 parameters
     float *d_scale = nullptr;        // folded BN: per layer 128 scale + 128 shift (tower), heads after
     // tcgen05 tower operands (built by ck_net_tc.cu)
@@ -41,6 +42,9 @@ struct ck_net {
     float *d_policy = nullptr, *d_value = nullptr;
     int64_t io_cap = 0;
     cudaEvent_t ev_after_tower = nullptr;   // profiling hook: recorded between tower and heads
+    int32_t *d_range_flag = nullptr; // set by the tensor-core kernels when an activation leaves the split-fp16 range
+    float *d_value_pre = nullptr;    // ck_net_forward_logits: receives the value head's pre-tanh output (else nullptr)
+    float *d_logits_out = nullptr;   // ck_net_forward_logits on the CUDA-core heads: receives the policy logits
 };
 
 namespace ck {
@@ -52,6 +56,9 @@ constexpr int kScaleValD1 = kScaleVal1x1 + 2;         // 64 scale, 64 shift
 constexpr int kScaleTotal = kScaleValD1 + 128;
 
 int net_reserve(ck_net *net, int64_t n, bool full_maps);
+// CK_ERR_NET_RANGE (and the flag cleared) if a tensor-core kernel of this net saw an activation beyond the split-fp16
+// range since the last check; synchronises the default stream's view of the flag with a blocking 4-byte copy
+int net_check_range(ck_net *net);
 // n_dev (optional): device pointer to the live row count; rows >= *n_dev are skipped
 int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
                      float *d_policy, float *d_value, cudaStream_t stream, int *launches);

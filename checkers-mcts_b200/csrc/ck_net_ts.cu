@@ -85,6 +85,7 @@ struct TowerParams {
     float *pflat;                // fp32 [n][512]: policy conv1x1 + ReLU + BN, flattened in (x, y, c) order
     float *vconv;                // fp32 [n][64]: value conv1x1 + ReLU + BN
     const float *plane5;         // 81-entry float32(n/80) table
+    int32_t *range_flag;         // set to 1 when an activation leaves the split-fp16 range (|a| * 2^4 >= 65504)
 };
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
@@ -291,6 +292,7 @@ tower_ts_kernel(const TowerParams prm) {
                 const float *bias_p = prm.blob + prm.bias_off[layer];
                 const uint32_t st_base = smem_u32(smem) + (uint32_t)(t * kTileBytes) + ((lane >> 4) ? (uint32_t)kSplitBytes : 0u) +
                                          (uint32_t)((4 * quad + ((lane >> 3) & 1)) * kChunkStride + sq_off(0, 1, (lane & 7) + 1));
+                __half2 amax = __float2half2_rn(0.f);           // range guard: largest |hi half| this thread wrote
                 float vp[16];                                   // value conv1x1 partial sums (conv6 epilogue only)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) vp[i] = 0.f;
@@ -318,6 +320,7 @@ tower_ts_kernel(const TowerParams prm) {
                         const __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
                         const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
                         const __half2 l0 = __floats2half2_rn(a0 - f0.x, a1 - f0.y), l1 = __floats2half2_rn(a2 - f1.x, a3 - f1.y);
+                        amax = __hmax2_nan(amax, __hmax2_nan(__habs2(h0), __habs2(h1)));
                         stmatrix_x4_trans(st_base + (uint32_t)(2 * h * kChunkStride + g * 160),
                                           *reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
                                           *reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
@@ -355,6 +358,11 @@ tower_ts_kernel(const TowerParams prm) {
                             if (pos0 + p < n) prm.vconv[(pos0 + p) * 64 + x * 8 + y] = fmaf(fmaxf(fmaf(sum, q, bv), 0.f), scv, shv);
                         }
                     }
+                }
+                // an activation beyond fp16's range became +-inf above (and its lo half NaN): never silent
+                {
+                    const uint32_t ab = *reinterpret_cast<const uint32_t *>(&amax);      // exponent all ones: inf or NaN
+                    if ((ab & 0x7C00u) == 0x7C00u || (ab & 0x7C000000u) == 0x7C000000u) atomicExch(prm.range_flag, 1);
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -497,6 +505,7 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     prm.bias_off[8] = L.pol1x1.bias;
     prm.val1x1_k = L.val1x1.kernel; prm.val1x1_b = L.val1x1.bias;
     prm.pflat = d_pflat; prm.vconv = d_vconv;
+    prm.range_flag = net->d_range_flag;
     const int rc = launch_tower_ts<8>(net, prm, max_n, stream);
     if (rc != CK_OK) return rc;
     if (launches) *launches += 1;

@@ -180,6 +180,15 @@ def _engine_cfg(mcts_kwargs, n_slots, terminate_cnt, evaluator, evaluator_p2=Non
                        arena=arena, keep_records=keep_records, game_id_base=game_id_base, game_id_stride=game_id_stride)
 
 
+def selfplay_workers(num_cpus):
+    """host processes that write the per-worker pickle files: NUM_CPUS of them, bounded by the host's cores"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return max(1, min(int(num_cpus), cores))
+
+
 def _np_empty(dtype):
     return np.zeros(0, dtype=dtype)
 
@@ -258,15 +267,19 @@ class generate_Checkers_data(object):
         for g in games:
             print('{} after {} moves!'.format(names[int(g["outcome"])], int(g["move_count"])))
         timestamp = create_timestamp()
-        filenames = []
-        for proc in range(self.num_cpus):                 # worker p played games [p*N, (p+1)*N)
-            lo, hi = proc * self.NUM_SELFPLAY_GAMES, (proc + 1) * self.NUM_SELFPLAY_GAMES
-            memory = _R.to_reference_list(recs[(recs["game"] >= lo) & (recs["game"] < hi)], playouts)
-            filenames.append(self._save_memory(memory, self.TRAINING_ITERATION, timestamp, proc))
+        # worker p played games [p*N, (p+1)*N) (:326-329); its file is converted to the reference's list format and
+        # pickled by a pool process (the conversion is numpy over whole record arrays, see ckb200.records)
+        bounds = np.searchsorted(recs["game"], np.arange(self.num_cpus + 1) * self.NUM_SELFPLAY_GAMES)
+        jobs = [(recs[bounds[p]:bounds[p + 1]], self._filename(self.TRAINING_ITERATION, timestamp, p)) for p in range(self.num_cpus)]
+        filenames = _R.save_reference_pickles(jobs, playouts, workers=selfplay_workers(self.num_cpus))
         return filenames if self.num_cpus > 1 else filenames[0]
 
+    @staticmethod
+    def _filename(iteration, timestamp, process_num):
+        return 'data/training_data/Checkers_Data' + str(iteration) + '_' + timestamp + '_P' + str(process_num) + '.pkl'
+
     def _save_memory(self, memory, iteration, timestamp, process_num):
-        filename = 'data/training_data/Checkers_Data' + str(iteration) + '_' + timestamp + '_P' + str(process_num) + '.pkl'
+        filename = self._filename(iteration, timestamp, process_num)
         with open(filename, 'wb') as file:
             pickle.dump(memory, file)
         return filename
@@ -317,7 +330,9 @@ class tournament_Checkers(object):
         rows = []
         for g in games:
             p1, p2 = (self.nn1_fn, self.nn2_fn) if int(g["p1_net"]) == 0 else (self.nn2_fn, self.nn1_fn)
-            rows.append([int(g["game"]) + 1, p1, p2, names[int(g["outcome"])], int(g["move_count"])])
+            # the reference strips the model folder from the names it records (:550-553)
+            rows.append([int(g["game"]) + 1, p1.replace('data/model/', ''), p2.replace('data/model/', ''),
+                         names[int(g["outcome"])], int(g["move_count"])])
         return rows
 
     def start_tournament(self):
@@ -401,8 +416,8 @@ class final_evaluation(object):
     def _parse_tourney_results(self):
         for game_outcomes in self.game_outcomes:
             for _game_num, p1_fn, p2_fn, outcome, _move_count in game_outcomes:
-                p1_idx = self.model_fn_list.index(os.path.basename(p1_fn))
-                p2_idx = self.model_fn_list.index(os.path.basename(p2_fn))
+                p1_idx = self.model_fn_list.index(p1_fn)
+                p2_idx = self.model_fn_list.index(p2_fn)
                 if outcome == 'player1_wins':
                     self.table[p1_idx, p2_idx] += 1
                     self.table[p2_idx, p1_idx] -= 1

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define CK_ABI_VERSION 1
+#define CK_ABI_VERSION 2
 #define CK_MAX_CHILDREN 48          /* 12 kings x 4 directions */
 #define CK_POLICY_SIZE 512          /* 8 action planes x 8 x 8 (Checkers.py:434) */
 #define CK_NET_PARAM_COUNT 1321774  /* create_nn, training_pipeline.py:44-120 */
@@ -26,7 +26,8 @@ extern "C" {
 enum { CK_ONGOING = 0, CK_P1_WINS = 1, CK_P2_WINS = 2, CK_DRAW = 3 };
 enum {
     CK_OK = 0, CK_ERR_CUDA = 1, CK_ERR_ARG = 2, CK_ERR_POOL_OVERFLOW = 3,
-    CK_ERR_DEPTH = 4, CK_ERR_STATE = 5, CK_ERR_NOMEM = 6, CK_ERR_NO_NET = 7
+    CK_ERR_DEPTH = 4, CK_ERR_STATE = 5, CK_ERR_NOMEM = 6, CK_ERR_NO_NET = 7,
+    CK_ERR_NET_RANGE = 8      /* a network activation left the range of the split-fp16 tensor-core path; results invalid */
 };
 
 /* Compact position.  Square s = 4*x + (y>>1) over the playable squares x%2 != y%2
@@ -103,6 +104,13 @@ int ck_net_set_weights(ck_net *, const float *blob, int64_t count);          /* 
 int ck_net_set_weights_device(ck_net *, const float *d_blob, int64_t count); /* device blob (e.g. a torch tensor) */
 /* raw softmax policy [n,512] and tanh value [n] (what Keras predict returns) */
 int ck_net_forward(ck_net *, const ck_leaf *leaves, int64_t n, float *policy, float *value);
+/* the same plus what north_star's 1e-5 contract is stated on: the policy logits [n,512] (input of the Dense softmax,
+ * training_pipeline.py:97-100) and the value head's pre-tanh output [n] (:111-112).  Any output pointer may be NULL. */
+int ck_net_forward_logits(ck_net *, const ck_leaf *leaves, int64_t n, float *policy, float *value, float *logits, float *value_pre);
+/* The tensor-core path keeps activations as split fp16 scaled by 2^4: a BatchNorm output with |a| >= 4094 does not
+ * fit.  The kernels flag it; the host entry points above return CK_ERR_NET_RANGE, the engine reports it from
+ * ck_engine_run, and after ck_net_forward_device the caller asks here (synchronises the device). */
+int ck_net_range_status(ck_net *);
 /* Keras signature: x float32 [n,8,8,14] channels-last (Checkers.py:431-433) */
 int ck_net_forward_planes(ck_net *, const float *x, int64_t n, float *policy, float *value);
 int ck_net_forward_device(ck_net *, const ck_leaf *d_leaves, int64_t n, float *d_policy, float *d_value,
@@ -145,6 +153,11 @@ typedef struct {
     int32_t game_id_stride;   /* 0 is treated as 1 */
     int32_t max_terminal_sims_per_step; /* simulations ending in a terminal child that a slot may finish inside one round; 0: default 4 */
     int32_t compact_always;   /* 1: compact the kept subtree at every re-root (default: only when the pool runs low) */
+    int32_t eval_cache_entries; /* evaluation cache entries per slot (128 B each, rounded up to a power of two); 0: default 4096;
+                                 * < 0: no cache.  A leaf whose network input (position, side to move, plane 5) was evaluated
+                                 * before in the same slot is expanded from the cached priors / value: same numbers, no network call */
+    int32_t max_chain_per_step; /* simulations a slot may complete inside one round without a network evaluation
+                                 * (terminal children + cache hits); 0: default 8 */
     int32_t reserved0;
 } ck_engine_cfg;
 
@@ -178,7 +191,7 @@ typedef struct {
 
 typedef struct {
     uint64_t sims;            /* root.selection() calls completed (MCTS.py:220,430) */
-    uint64_t nn_evals;        /* leaf evaluations */
+    uint64_t nn_evals;        /* leaf evaluations (expansions), including those served by the evaluation cache */
     uint64_t steps;           /* tree-step + eval rounds executed */
     uint64_t games_finished;
     uint64_t moves;
@@ -188,6 +201,7 @@ typedef struct {
     double   eval_ms;         /* of which inside the evaluator kernels (profile mode; else 0) */
     double   tower_ms;        /* of which inside the tcgen05 tower kernel (profile mode; else 0) */
     uint64_t kernel_launches;
+    uint64_t cache_hits;      /* expansions served by the evaluation cache: network evaluations run = nn_evals - cache_hits */
 } ck_run_stats;
 
 typedef struct ck_engine ck_engine;

@@ -15,8 +15,10 @@ import torch.nn.functional as F
 BN_EPS = 1e-3
 
 
-def forward(params, x, dtype=torch.float64):
-    """params: dict from ckb200.net.unpack; x: [n,8,8,14] channels-last -> (policy [n,512], value [n])."""
+def forward(params, x, dtype=torch.float64, pre_activation=False):
+    """params: dict from ckb200.net.unpack; x: [n,8,8,14] channels-last -> (policy [n,512], value [n]);
+    with ``pre_activation`` also the policy logits [n,512] (before the softmax) and the value head's
+    pre-tanh output [n] -- the quantities north_star's 1e-5 contract is stated on."""
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
 
     def bn(h, name, dim):
@@ -35,11 +37,15 @@ def forward(params, x, dtype=torch.float64):
         h = conv(h, "conv%d" % i)
     p = conv(conv(h, "policy_conv1"), "policy_conv2")
     p = p.permute(0, 2, 3, 1).reshape(len(x), 512)                 # Flatten over (x, y, c)
-    p = torch.softmax(p @ t(params["policy_head/kernel"]) + t(params["policy_head/bias"]), dim=1)
+    logits = p @ t(params["policy_head/kernel"]) + t(params["policy_head/bias"])
+    p = torch.softmax(logits, dim=1)
     v = conv(h, "value_conv1").permute(0, 2, 3, 1).reshape(len(x), 64)
     v = F.relu(v @ t(params["value_dense1/kernel"]) + t(params["value_dense1/bias"]))
     v = bn(v, "value_dense1", 1)
-    v = torch.tanh(v @ t(params["value_head/kernel"]) + t(params["value_head/bias"]))
+    vpre = v @ t(params["value_head/kernel"]) + t(params["value_head/bias"])
+    v = torch.tanh(vpre)
+    if pre_activation:
+        return p.numpy(), v.reshape(-1).numpy(), logits.numpy(), vpre.reshape(-1).numpy()
     return p.numpy(), v.reshape(-1).numpy()
 
 

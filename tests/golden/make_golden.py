@@ -11,6 +11,14 @@ Outputs (all small, committed):
   mcts_kat.json       KAT-A / KAT-B / hash-stub first searches + per-move root statistics
   selfplay_*.npz      full records of _generate_data run verbatim with stub nets
   tournament.json     _start_tournament run verbatim with two different stub nets
+  net_model10.npz, net_model5.npz
+                      the reference's own trained networks data/model/Checkers_Model{10,5}_*.h5 (read with
+                      ckb200.h5lite): the float32 weight blob, 256 positions from uniformly random play, and the
+                      float64 restatement's policy logits / pre-tanh value / softmax / tanh on them
+                      (python tests/golden/make_golden.py net  regenerates only these)
+  tournament_results.json
+                      W/L/D of the reference's own evaluation tournaments (data/tournament_results/Tournament*.txt)
+                      and its final round-robin table (data/final_eval/*.txt), parsed
   uct_kat.json        NEURAL_NET=False (UCT + one playout per simulation, the iteration-0 mode): first search
                       and per-move root statistics of a _generate_data game, with np.random.randint inside
                       MCTS.default_policy replaced by a hash of the position the move is chosen from
@@ -300,8 +308,75 @@ def make_tournament(workdir):
     print("tournament:", outcomes)
 
 
+def random_play_leaves(n, seed):
+    """positions reached by uniformly random legal play (oracle rules, pinned to the reference by the movegen
+    goldens above) -> (leaves as LEAF_DTYPE-compatible uint32 [n,12], NN input planes float32 [n,8,8,14])"""
+    from oracle import oracle as O
+    rng = np.random.RandomState(seed)
+    leaves = np.zeros((n, 12), dtype=np.uint32)
+    planes = np.zeros((n, 8, 8, 14), dtype=np.float32)
+    i = 0
+    while i < n:
+        pos = O.start_position()
+        for _ply in range(rng.randint(1, 140)):
+            kids, mask, st, p5 = O.movegen(pos)
+            if st != codec.ONGOING:
+                break
+            pos = kids[rng.randint(len(kids))]
+        kids, mask, st, p5 = O.movegen(pos)
+        if st != codec.ONGOING:
+            continue
+        leaves[i] = [pos[0], pos[1], pos[2], (pos[3] & 1) | (p5 << 8)] + list(mask)
+        planes[i] = codec.nn_input_planes(pos, mask, p5)
+        i += 1
+    return leaves, planes
+
+
+def make_net():
+    """trained-weight fixtures for K3 (the reference ships 11 networks, training_pipeline.py:345,515-516)"""
+    import glob
+    from ckb200 import h5lite
+    from ckb200 import net as N
+    from oracle import net_oracle as NO
+    leaves, planes = random_play_leaves(256, 20261018)
+    for it in (10, 5):
+        fn = glob.glob(os.path.join(H.REFERENCE_DIR, "data", "model", "Checkers_Model%d_*.h5" % it))[0]
+        blob = h5lite.keras_h5_to_blob(fn)
+        pol, val, logits, vpre = NO.forward(N.unpack(blob), planes, pre_activation=True)
+        np.savez_compressed(os.path.join(HERE, "net_model%d.npz" % it), blob=blob.astype(np.float32), leaves=leaves,
+                            policy=pol, value=val, logits=logits, value_pre=vpre, source=os.path.basename(fn))
+        print("net golden", os.path.basename(fn), "max|logit|", float(np.abs(logits).max()), "max|vpre|", float(np.abs(vpre).max()))
+
+
+def make_tournament_results():
+    """the reference's recorded evaluation results, parsed (which iteration beat which): the statistical pin of the
+    network semantics -- a replay of a pairing on the engine has to land in the same place"""
+    import glob
+    import re
+    out = {"tournaments": [], "final_eval": None}
+    for fn in sorted(glob.glob(os.path.join(H.REFERENCE_DIR, "data", "tournament_results", "Tournament*.txt"))):
+        rows = re.findall(r"Checkers_Model(\d+)_[^ ]+\.h5\s*\u2502\s*(\d+)/(\d+)/(\d+)", open(fn, encoding="utf-8").read())
+        (a, w, l, d), (b, _, _, _) = rows[0], rows[1]
+        out["tournaments"].append(dict(file=os.path.basename(fn), new=int(a), old=int(b), wins=int(w), losses=int(l), draws=int(d)))
+    fe = glob.glob(os.path.join(H.REFERENCE_DIR, "data", "final_eval", "Checkers_Final_Evaluation_*.txt"))
+    fe = [f for f in fe if "Params" not in f]
+    if fe:
+        table = []
+        for line in open(fe[0], encoding="utf-8"):
+            cells = [c.strip() for c in line.split("\u2502")[1:-1]]
+            if len(cells) == 13 and cells[0].isdigit():
+                table.append([int(c) for c in cells[1:]])
+        out["final_eval"] = dict(file=os.path.basename(fe[0]), budget=400, table=table)
+    json.dump(out, open(os.path.join(HERE, "tournament_results.json"), "w"), indent=1)
+    print("tournament results:", [(t["new"], t["old"], t["wins"], t["losses"], t["draws"]) for t in out["tournaments"]])
+
+
 def main():
     assert H.reference_available(), "reference not mounted"
+    if sys.argv[1:] == ["net"]:
+        make_net()
+        make_tournament_results()
+        return
     workdir = tempfile.mkdtemp(prefix="ckref_")
     os.makedirs(os.path.join(workdir, "data/training_data"))
     os.makedirs(os.path.join(workdir, "data/tournament_results"))

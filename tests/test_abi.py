@@ -33,7 +33,7 @@ def test_header_symbols_exported(built):
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     L.ck_abi_version.restype = C.c_int
-    assert L.ck_abi_version() == 1
+    assert L.ck_abi_version() == 2
 
 
 def test_binding_struct_sizes(built):

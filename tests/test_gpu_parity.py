@@ -299,6 +299,64 @@ def test_concurrent_games_vs_oracle(lib, slots, compact):
     eng.close()
 
 
+@pytest.mark.parametrize("cache,chain", [(-1, 0), (16, 1), (64, 3), (0, 0), (0, 64)])
+def test_eval_cache_is_transparent(lib, cache, chain):
+    """the evaluation cache (a leaf whose network input was evaluated before in the same slot is expanded from the
+    stored priors / value inside the round) must not change a single bit of any record: no cache, a 16-entry cache
+    that evicts all the time, the default, different per-round chain caps -- all equal the oracle, which evaluates
+    every leaf.  Games follow each other in a slot, so entries of a finished game are probed by the next one
+    (salted evaluator: they must not hit)."""
+    n_games, budget, term = 12, 64, 60
+    ref = _oracle_games(n_games, budget, term)
+    eng = lib.Engine(lib.make_cfg(n_slots=3, budget=budget, training=True, terminate_cnt=term, evaluator="hash_salted",
+                                  eval_cache_entries=cache, max_chain_per_step=chain))
+    st = eng.selfplay(n_games)
+    recs, games = _engine_records(lib, eng)
+    for g in range(n_games):
+        rr, outcome, move_count, terminated, sims, evals = ref[g]
+        assert int(games[g]["outcome"]) == outcome and int(games[g]["move_count"]) == move_count
+        assert int(games[g]["sims"]) == sims and int(games[g]["nn_evals"]) == evals
+        assert len(recs[g]) == len(rr) and all(_same_record(a, b) for a, b in zip(recs[g], rr))
+    if cache < 0:
+        assert st["cache_hits"] == 0
+    else:
+        assert 0 < st["cache_hits"] < st["nn_evals"]
+        if cache == 0:
+            assert st["cache_hits"] > 0.2 * st["nn_evals"]      # the two colours' trees repeat each other's evaluations
+    eng.close()
+
+
+def test_eval_cache_with_network_and_weight_change(lib):
+    """network evaluator: identical records with and without the cache (noise and temperature on), and new weights on
+    the same net object invalidate the cached evaluations"""
+    from ckb200 import net as N
+    net = lib.Net(0)
+
+    def run(blob_seed, cache):
+        net.set_weights(N.random_init_blob(blob_seed))
+        eng = lib.Engine(lib.make_cfg(n_slots=16, budget=100, training=True, terminate_cnt=6, evaluator="net", uct_c=4.0, alpha=1.0,
+                                      epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=5, eval_cache_entries=cache))
+        eng.set_net(0, net)
+        st = eng.selfplay(16)
+        recs = eng.records()
+        out = [st, recs[np.lexsort((recs["ply"], recs["game"]))]]
+        # second batch of games on the SAME engine after a weight change: stale entries must not be used
+        net.set_weights(N.random_init_blob(blob_seed + 1))
+        st2 = eng.selfplay(16)
+        recs = eng.records()
+        out += [st2, recs[np.lexsort((recs["ply"], recs["game"]))]]
+        eng.close()
+        return out
+
+    a = run(0, -1)
+    b = run(0, 0)
+    assert a[1].tobytes() == b[1].tobytes() and a[3].tobytes() == b[3].tobytes()
+    assert a[1].tobytes() != a[3].tobytes()                      # the two weight sets do play differently
+    assert a[0]["cache_hits"] == 0 and b[0]["cache_hits"] > 0 and b[2]["cache_hits"] > 0
+    assert a[0]["nn_evals"] == b[0]["nn_evals"] and a[0]["sims"] == b[0]["sims"]
+    net.close()
+
+
 def test_uct_first_search_golden_and_midgame_vs_oracle(lib):
     """NEURAL_NET=False tree policy (MCTS.py:78-89,113-115): one child per visit, UCT in float64, one playout
     per simulation.  With hashed playouts the whole search is deterministic: the reference's own first search
