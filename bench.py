@@ -1,16 +1,22 @@
 #!/usr/bin/env python3
-"""bench.py -- MCTS simulations/s of batched Checkers self-play on B200 (BASELINE.json metric).
+"""bench.py -- MCTS simulations/s and self-play games/s of batched Checkers self-play on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA arm
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: oracle port on the host cores
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's own code on the host cores
 
-Workload (BASELINE.json configs[1]): 4096 concurrent self-play games per GPU, 400 sims/move,
-UCT_C=4, Dirichlet(alpha=1, eps=0.25) at every node, tau=1 with decay, TERMINATE_CNT=200,
-random-init network (seed 0), games start from the initial position and are refilled when they
-finish.  One "step" = 400 lock-step rounds (tree kernel + batched network evaluation), i.e. about
-one move of every game.  `value` = simulations completed / device time (CUDA events on the engine's
-stream), inputs resident in HBM.  `e2e` = the same metric through the host-buffer API: every step
-uploads the weight blob from pinned host memory and reads the finished games' records back.
+Workload (BASELINE.json configs[1]): 4096 concurrent self-play games per GPU, 400 sims/move, UCT_C=4,
+Dirichlet(alpha=1, eps=0.25) at every node, tau=1 with decay, TERMINATE_CNT=200, random-init network (seed 0); slots
+are refilled when their game ends.  One "step" = 400 lock-step rounds (tree kernel + batched network evaluation).
+
+Steady state: before the warm-up the slots are desynchronised by an untimed pre-roll at a tiny budget (games end and
+restart at scattered times), so the timed region sees games at every stage, finishing games included, instead of 4096
+openings in lock step.  Then 2K steps alternate:
+  even steps -> `value`: simulations / device time (CUDA events on the engine's stream), inputs resident in HBM;
+  odd steps  -> `e2e`: the same loop through the host-buffer C ABI, wall clock: the weight blob goes up from pinned host
+                memory (H2D), the step runs, the finished games' records and results come back (D2H).
+`games_per_sec` = games finished in the even steps / their device time.  `e2e_pipeline` (rank-local, after the timed
+region) = wall clock of the drop-in call a user of the reference makes, `generate_Checkers_data(...).generate_data()`
+(training_pipeline.py:312-332), for one batch of games played to the end INCLUDING the reference-format pickle files.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -34,6 +40,9 @@ UNIT = "sims/s"
 SLOTS = 4096
 BUDGET = 400
 ROUNDS_PER_STEP = 400
+PREROLL_BUDGET = 8            # sims/move of the untimed pre-roll that desynchronises the slots
+PREROLL_ROUNDS = 2400         # ~3 game lengths at that budget
+REF_PLIES = 4                 # plies per game of a reference-arm sample (the reference's TERMINATE_CNT knob)
 TOWER_FLOP_PER_POS = 2 * (9 * 14 * 128 * 64 + 7 * 9 * 128 * 128 * 64 + 128 * 8 * 64)   # 134,316,032: the eight 3x3 convs + the policy conv1x1 the tower kernel evaluates
 NET_FLOP_PER_POS = 134865024                                               # SURVEY 8(d), whole network
 MCTS = dict(uct_c=4.0, training=True, alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10,
@@ -166,42 +175,150 @@ def cpu_port_sample(n_procs, seconds, budget=BUDGET, pool=None):
     return sims / el, n_procs, sims, el
 
 
+def reference_sample(cpus, plies, budget=BUDGET, timeout=900):
+    """one bounded sample of the reference's OWN self-play code (oracle/_ref byte code, see oracle/ref_arm.py) in a fresh
+    process: `cpus` worker processes through its mp.Pool fan-out, one game each, adjudicated after `plies` plies.
+    -> dict(sims, seconds, sims_per_sec, cores, ...) or None when the compiled reference is not available"""
+    from oracle import build_ref
+    if not build_ref.available() and not os.path.isfile(os.path.join(build_ref.REFERENCE_DIR, "Checkers.py")):
+        return None
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "--cpus", str(cpus), "--plies", str(plies), "--budget", str(budget)],
+                       cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    sys.stderr.write("reference sample failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return None
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the reference's algorithm (oracle port) on all host cores, one process per core
-    like the reference's own mp.Pool.map fan-out (training_pipeline.py:326-329)."""
+    """CPU arm.  Preferred: the reference's own implementation (kind "reference"): its generate_data() with its own
+    mp.Pool.map fan-out over every host core (training_pipeline.py:323-332), game loop, MCTS and rules, byte-compiled
+    from /root/reference into oracle/_ref at build time; only Keras is replaced by a torch-CPU stand-in.  Each step
+    is a bounded sample: one game per core cut after REF_PLIES plies (the reference's TERMINATE_CNT) at 400 sims/move.
+    Fallback when oracle/_ref was not built: the oracle port (kind "port")."""
     if rank != 0:
         return
-    import multiprocessing as mp
-    from oracle import oracle as O
-    O.build()
     cores = usable_cores()
-    per_step = 6.0
-    with mp.get_context("spawn").Pool(cores) as pool:
-        for _ in range(args.warmup):
-            cpu_port_sample(cores, 1.0, pool=pool)
-        vals = []
-        t0 = time.time()
-        for _ in range(args.steps):
-            v, c, sims, el = cpu_port_sample(cores, per_step, pool=pool)
-            vals.append(v)
-        wall = time.time() - t0
+    vals, kind, sample = [], "reference", ""
+    t0 = time.time()
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            t0 = time.time()
+        r = reference_sample(cores, REF_PLIES)
+        if r is None:
+            kind = "port"
+            break
+        if i >= args.warmup:
+            vals.append(r["sims_per_sec"])
+        cores = r["cores"]
+        sample = ("the reference's own generate_data(): %d worker processes (mp.Pool.map) x 1 self-play game cut after %d plies "
+                  "(TERMINATE_CNT) at %d sims/move, torch-CPU stand-in for Keras (1 thread per worker, random-init weights); "
+                  "%d sims in %.1f s per step" % (r["cores"], REF_PLIES, BUDGET, r["sims"], r["seconds"]))
+    if kind == "port":
+        import multiprocessing as mp
+        from oracle import oracle as O
+        O.build()
+        per_step = 6.0
+        with mp.get_context("spawn").Pool(cores) as pool:
+            for _ in range(args.warmup):
+                cpu_port_sample(cores, 1.0, pool=pool)
+            t0 = time.time()
+            for _ in range(args.steps):
+                v, c, sims, el = cpu_port_sample(cores, per_step, pool=pool)
+                vals.append(v)
+        sample = ("oracle port (C tree + torch-CPU net, batch-1 eval), %d processes x %.0f s of self-play at %d sims/move per step"
+                  % (cores, per_step, BUDGET))
+    wall = time.time() - t0
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "oracle port (C tree + torch-CPU net, batch-1 eval), %d processes x %.0f s of self-play "
-                                       "at %d sims/move per step" % (cores, per_step, BUDGET)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
+def pipeline_e2e(dev, rank, world, n_games, num_cpus):
+    """wall clock of the reference-facing call, generate_Checkers_data(...).generate_data() (training_pipeline.py:312-332):
+    `n_games` self-play games at cfg2 settings played to the end on this rank's GPU, records converted to the reference's
+    [state, probs, q, z] lists and pickled into data/training_data/ like the reference's workers do.  Rank-local (every
+    rank plays its own batch: the weak-scaling shape of the bench), files go to a scratch directory and are removed."""
+    import shutil
+    import tempfile
+    import training_pipeline as TP
+    from ckb200 import net as N
+    work = tempfile.mkdtemp(prefix="ckb200_pipe_%d_" % rank)
+    free = shutil.disk_usage(work).free
+    need = n_games * 150 * 12000 * 1.2                      # ~150 records per game x 11.8 KB in the reference's format
+    if free < need:
+        n_games = max(num_cpus, int(n_games * free / need / num_cpus) * num_cpus)
+    os.makedirs(os.path.join(work, "data", "training_data"))
+    os.makedirs(os.path.join(work, "data", "model"))
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        fn = TP.save_blob(N.random_init_blob(0), "data/model/Checkers_Model0_bench.npy")
+        sp = dict(NUM_SELFPLAY_GAMES=n_games // num_cpus, TRAINING_ITERATION=0, TERMINATE_CNT=MCTS["terminate_cnt"], NUM_CPUS=num_cpus,
+                  NN_FN=fn, DEVICE=dev, SEED=20261017 + rank, MAX_CONCURRENT_GAMES=SLOTS, SINGLE_PROCESS=True)
+        mk = dict(UCT_C=4, CONSTRAINT='rollout', BUDGET=BUDGET, MULTIPROC=False, NEURAL_NET=True, VERBOSE=False, TRAINING=True,
+                  DIRICHLET_ALPHA=1.0, DIRICHLET_EPSILON=0.25, TEMPERATURE_TAU=1.0, TEMPERATURE_DECAY=0.1, TEMP_DECAY_DELAY=10)
+        gen = TP.generate_Checkers_data(sp, mk)
+        t0 = time.time()
+        with open(os.devnull, "w") as devnull:
+            saved = sys.stdout
+            sys.stdout = devnull                             # the reference prints one line per finished game
+            try:
+                files = gen.generate_data()
+            finally:
+                sys.stdout = saved
+        wall = time.time() - t0
+        files = [files] if isinstance(files, str) else files
+        nbytes = sum(os.path.getsize(f) for f in files)
+        st = gen.stats
+        return {"value": st["sims"] / wall, "unit": UNIT, "call": "generate_Checkers_data(selfplay_kwargs, mcts_kwargs).generate_data()",
+                "games": n_games, "workers_NUM_CPUS": num_cpus, "wall_s": wall, "gpu_s": st["gpu_ms"] / 1e3,
+                "host_s_after_gpu": gen.host_seconds, "host_share_of_gpu_time": gen.host_seconds / max(st["gpu_ms"] / 1e3, 1e-9),
+                "sims": st["sims"], "games_per_sec": n_games / wall, "records": gen.n_records, "pickle_bytes": nbytes, "files": len(files)}
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def verify_sharding(dev, rank, world):
+    """world > 1, outside the timed region: V games per rank at a small budget, sharded game g -> rank g mod world as
+    in the bench, pooled on rank 0 with the packed device-side gather; rank 0 then replays ALL of them in one
+    single-process engine and compares the pooled records byte for byte (a game's random streams are keyed by its
+    global index, so the shards of an N-rank run must equal a 1-rank run)."""
+    from ckb200 import dist as D
+    from ckb200 import lib as L
+    per_rank, budget, term = 32, 64, 24
+    total = per_rank * world
+    kw = dict(budget=budget, device=dev, evaluator="hash_salted", keep_records=True, seed=77, uct_c=4.0, training=True, alpha=1.0,
+              epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10, terminate_cnt=term)
+    base, stride, n_local = D.shard(total, rank, world)
+    eng = L.Engine(L.make_cfg(n_slots=per_rank, game_id_base=base, game_id_stride=stride, **kw))
+    eng.selfplay(n_local)
+    pooled, _ms = D.gather_engine_records(eng, rank, world, "cuda:%d" % dev)
+    eng.close()
+    if rank != 0:
+        return None
+    eng = L.Engine(L.make_cfg(n_slots=total, **kw))
+    eng.selfplay(total)
+    single = eng.records()
+    eng.close()
+    key = lambda r: r[np.lexsort((r["ply"], r["game"]))]
+    a, b = key(pooled), key(single)
+    return {"games": total, "records": int(len(b)), "identical": bool(len(a) == len(b) and a.tobytes() == b.tobytes())}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+    from ckb200 import dist as D
     from ckb200 import lib as L
     from ckb200 import net as N
     L.require_device()
@@ -215,15 +332,14 @@ def run_ours(args, rank, world, local_rank):
     weights.copy_(pinned)
     net.set_weights_device(weights.data_ptr(), weights.numel())
 
-    from ckb200 import dist as D
     base, stride, _n = D.shard(args.slots * world, rank, world)          # game g -> rank g mod world
     cfg = L.make_cfg(n_slots=args.slots, budget=BUDGET, device=dev, evaluator="net", keep_records=True,
-                     seed=20261017, game_id_base=base, game_id_stride=stride, **MCTS)
+                     seed=20261017, game_id_base=base, game_id_stride=stride,
+                     eval_cache_entries=-1 if args.no_eval_cache else 0, **MCTS)
     eng = L.Engine(cfg)
     eng.set_net(0, net)
-    n_games = args.slots * 8                     # staged games: enough refills for any bench length
+    n_games = args.slots * 16                    # staged games: enough refills for the pre-roll and any bench length
     eng.begin(n_games)
-    eng.set_profile(True)
     rec_buf = np.zeros(args.slots * 201, dtype=L.RECORD_DTYPE)
 
     def barrier():
@@ -231,63 +347,80 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- untimed: desynchronise the slots (pre-roll at a tiny budget), then warm up at the real one ----------
+    pre = dict(rounds=0, games=0, moves=0)
+    if args.preroll > 0:
+        eng.set_budget(PREROLL_BUDGET)
+        st = eng.run(args.preroll)
+        pre = dict(rounds=int(st["steps"]), games=int(st["games_finished"]), moves=int(st["moves"]))
+        eng.set_budget(BUDGET)
+        eng.records_new(rec_buf)                  # the pre-roll's records are not the bench's
     for _ in range(args.warmup):
         eng.run(args.rounds)
+        eng.records_new(rec_buf)
+    eng.set_profile(True)
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
 
-    # ---- timed region 1: device-resident throughput --------------------------------------------
+    # ---- timed region: device-resident steps and end-to-end steps alternate, so both see the same game phases ----
+    keys = ("sims", "nn_evals", "cache_hits", "gpu_ms", "eval_ms", "tower_ms", "kernel_launches", "games_finished", "moves", "steps")
+    agg = {k: 0 for k in keys}
+    e = dict(sims=0, h2d=0, d2h=0, ms=0.0, launches=0, games=0, records=0)
     barrier()
     t0 = time.time()
-    agg = dict(sims=0, nn_evals=0, gpu_ms=0.0, eval_ms=0.0, tower_ms=0.0, kernel_launches=0, games_finished=0, moves=0, steps=0)
     for _ in range(args.steps):
-        st = eng.run(args.rounds)
-        for k in agg:
+        st = eng.run(args.rounds)                                           # device-resident step
+        for k in keys:
             agg[k] += st[k]
-    barrier()
-    wall = time.time() - t0
-
-    # ---- timed region 2: end to end through host buffers --------------------------------------
-    barrier()
-    e_t0 = time.time()
-    e_sims, e_h2d, e_d2h, e_ms, e_launch = 0, 0, 0, 0.0, 0
-    for _ in range(args.steps):
-        s0 = time.time()
-        weights.copy_(pinned, non_blocking=False)                       # H2D of this step's input (weights)
+        torch.cuda.synchronize()
+        s0 = time.time()                                                    # end-to-end step through host buffers
+        weights.copy_(pinned, non_blocking=False)                           # H2D: this step's input (the weights)
         net.set_weights_device(weights.data_ptr(), weights.numel())
         st = eng.run(args.rounds)
-        nrec, ngames = eng.records_new(rec_buf)                          # D2H of this step's results
-        e_sims += st["sims"]
-        e_launch += st["kernel_launches"]
-        e_h2d += blob.nbytes
-        e_d2h += nrec * L.RECORD_DTYPE.itemsize + n_games * L.GAME_DTYPE.itemsize
+        nrec, ngames = eng.records_new(rec_buf)                             # D2H: this step's results
         torch.cuda.synchronize()
-        e_ms += 1000.0 * (time.time() - s0)
+        e["ms"] += 1000.0 * (time.time() - s0)
+        e["sims"] += st["sims"]; e["launches"] += st["kernel_launches"]; e["games"] += ngames; e["records"] += nrec
+        e["h2d"] += blob.nbytes
+        e["d2h"] += nrec * L.RECORD_DTYPE.itemsize + n_games * L.GAME_DTYPE.itemsize
     barrier()
-    e_wall = time.time() - e_t0
+    wall = time.time() - t0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks: time = max, work = sum ----------------------------------------------
-    t = torch.tensor([agg["gpu_ms"], e_ms], dtype=torch.float64, device="cuda:%d" % dev)
-    w = torch.tensor([agg["sims"], agg["nn_evals"], agg["games_finished"], agg["moves"], e_sims, agg["kernel_launches"] + e_launch],
-                     dtype=torch.float64, device="cuda:%d" % dev)
+    t = torch.tensor([agg["gpu_ms"], e["ms"]], dtype=torch.float64, device="cuda:%d" % dev)
+    w = torch.tensor([agg["sims"], agg["nn_evals"], agg["games_finished"], agg["moves"], e["sims"], agg["kernel_launches"] + e["launches"],
+                      agg["cache_hits"], e["games"]], dtype=torch.float64, device="cuda:%d" % dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
     gpu_ms, e2e_ms = t.tolist()
-    sims, evals, games, moves, e2e_sims, launches = w.tolist()
+    sims, evals, games, moves, e2e_sims, launches, hits, e2e_games = w.tolist()
 
-    # pool finished records on rank 0 (the iteration-end NCCL gather; outside the timed regions)
-    gather_ms, pooled = None, None
+    # ---- outside the timed region ------------------------------------------------------------------
+    gather_ms, pooled_n, gather_bytes, shard_check = None, None, None, None
     if world > 1:
-        from ckb200 import dist as D
-        recs = eng.records()
-        torch.cuda.synchronize()
-        g0 = time.time()
-        pooled = D.gather_records(recs, rank, world, device="cuda:%d" % dev)
-        torch.cuda.synchronize()
-        gather_ms = 1000.0 * (time.time() - g0)
+        # the iteration-end NCCL gather of the finished games' records, packed on the device (ckb200.dist)
+        pooled, info = D.gather_engine_records(eng, rank, world, "cuda:%d" % dev, want_info=True)
+        if rank == 0:
+            gather_ms, pooled_n, gather_bytes = info["ms"], int(len(pooled)), info["bytes"]
+        del pooled
+    eng.close()
+    if world > 1:
+        shard_check = verify_sharding(dev, rank, world)
+    pipe = None
+    if not args.no_pipeline:
+        pipe = pipeline_e2e(dev, rank, world, args.pipeline_games, args.pipeline_workers)
+        if world > 1:
+            pv = torch.tensor([pipe["wall_s"]], dtype=torch.float64, device="cuda:%d" % dev)
+            pw = torch.tensor([pipe["sims"], pipe["games"], pipe["records"]], dtype=torch.float64, device="cuda:%d" % dev)
+            dist.all_reduce(pv, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pw, op=dist.ReduceOp.SUM)
+            pipe["wall_s_max_over_ranks"] = float(pv.item())
+            pipe["value"] = float(pw[0].item()) / float(pv.item())
+            pipe["games_all_ranks"], pipe["records_all_ranks"] = int(pw[1].item()), int(pw[2].item())
+            pipe["games_per_sec"] = pipe["games_all_ranks"] / float(pv.item())
 
     if rank != 0:
         return
@@ -297,25 +430,39 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f32 (split-fp16 tensor-core passes, fp32 accumulate)" if args.net_impl == "tc" else "f32",
             "data": "synthetic", "config": workload_config(world)}
     line["config"]["net_impl"] = args.net_impl
+    line["config"]["eval_cache"] = "off" if args.no_eval_cache else "on (per-slot, 4096 entries)"
+    line["config"]["steady_state"] = ("untimed pre-roll of %d rounds at %d sims/move desynchronises the slots (%d games finished and were "
+                                      "replaced, %d moves), then %d warm-up steps at %d sims/move" %
+                                      (pre["rounds"], PREROLL_BUDGET, pre["games"], pre["moves"], args.warmup, BUDGET))
     line["wall_s"] = wall
-    line["nn_evals_per_sec"] = evals / (gpu_ms / 1000.0)
+    line["nn_evals_per_sec"] = (evals - hits) / (gpu_ms / 1000.0)
+    line["expansions_per_sec"] = evals / (gpu_ms / 1000.0)
+    line["eval_cache_hit_rate"] = hits / max(evals, 1.0)
     line["moves_per_sec"] = moves / (gpu_ms / 1000.0)
     line["games_finished"] = games
+    line["games_per_sec"] = games / (gpu_ms / 1000.0)
     line["games_per_sec_est"] = (moves / (gpu_ms / 1000.0)) / 150.0      # at the ~150 plies/game BASELINE.md assumes
-    line["e2e"] = {"value": e2e_sims / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": e_h2d // max(args.steps, 1),
-                   "d2h_bytes_per_step": e_d2h // max(args.steps, 1), "wall_s": e_wall}
+    line["e2e"] = {"value": e2e_sims / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": e["h2d"] // max(args.steps, 1),
+                   "d2h_bytes_per_step": e["d2h"] // max(args.steps, 1), "games_per_sec": e2e_games / (e2e_ms / 1000.0),
+                   "games_finished": e2e_games, "how": "alternates with the device-timed steps; wall clock of H2D weights + 400 rounds + D2H records"}
+    if pipe is not None:
+        line["e2e_pipeline"] = pipe
     line["gpu_launches"] = int(launches)
     line["clocks"] = clocks
     if gather_ms is not None:
         line["records_gather_ms"] = gather_ms
-        line["records_pooled"] = int(len(pooled))
+        line["records_pooled"] = pooled_n
+        line["records_gather_bytes"] = gather_bytes
+    if shard_check is not None:
+        line["sharding_check"] = shard_check
 
     # roofline of the dominant kernel (the tcgen05 tower; rank 0's own launches)
     peaks = measured_peaks()
     n_launch = agg["steps"]
+    net_evals = agg["nn_evals"] - agg["cache_hits"]
     if args.net_impl == "tc" and agg["tower_ms"] > 0:
         peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
-        achieved = agg["nn_evals"] * TOWER_FLOP_PER_POS / (agg["tower_ms"] / 1000.0) / 1e12
+        achieved = net_evals * TOWER_FLOP_PER_POS / (agg["tower_ms"] / 1000.0) / 1e12
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "tower_ncu_summary.json"))).get("dram_bytes_per_launch")
@@ -324,29 +471,41 @@ def run_ours(args, rank, world, local_rank):
         line["roofline"] = {"bound": "tensor", "kernel": "tower_ts_kernel" if (os.environ.get("CK_TOWER") or "ts")[0] != "s" else "tower_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak, "traffic": traffic,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
-                            "flop_per_position": TOWER_FLOP_PER_POS, "positions_per_launch": agg["nn_evals"] / max(n_launch, 1),
+                            "flop_per_position": TOWER_FLOP_PER_POS, "positions_per_launch": net_evals / max(n_launch, 1),
                             "avg_launch_ms": agg["tower_ms"] / max(n_launch, 1),
                             "share_of_step": agg["tower_ms"] / max(agg["gpu_ms"], 1e-9),
                             "issued_mma_tflops": 3 * achieved, "issued_mma_frac_of_peak": 3 * achieved / peak,
-                            "note": "achieved/frac count useful FLOPs only (SURVEY 8d); the kernel issues 3 fp16 MMA passes per product "
-                                    "(split hi/lo operands) to meet the 1e-5 accuracy contract, so against the pipe's own peak frac is "
-                                    "bounded by 1/3; issued_mma_* is the tensor-pipe work actually executed.  The denominator is the "
-                                    "power-capped cuBLAS bf16 rate, which this kernel can exceed (it holds a higher clock)"}
+                            "note": "achieved/frac count useful FLOPs of EVALUATED positions only (SURVEY 8d); expansions served by the "
+                                    "evaluation cache cost no FLOPs and are not counted.  The kernel issues 3 fp16 MMA passes per product "
+                                    "(split hi/lo operands) for fp32-grade accuracy, so against the pipe's own peak frac is bounded by 1/3; "
+                                    "issued_mma_* is the tensor-pipe work actually executed.  The denominator is the power-capped cuBLAS "
+                                    "bf16 rate, which this kernel can exceed (it holds a higher clock)"}
     else:
         peak = 75.0
-        achieved = agg["nn_evals"] * NET_FLOP_PER_POS / (max(agg["eval_ms"], 1e-9) / 1000.0) / 1e12
+        achieved = net_evals * NET_FLOP_PER_POS / (max(agg["eval_ms"], 1e-9) / 1000.0) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "conv3x3_simt_kernel (CUDA-core cross-check path)", "achieved": achieved,
                             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                             "peak_source": "nominal fp32 CUDA-core rate; this path is not the product kernel"}
 
-    # CPU baseline (oracle port) on this box's host cores, bounded sample
+    # CPU baseline on this box's host cores, bounded samples: the reference's own code on all cores and on one
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        O.build()
-        v, c, s, el = cpu_port_sample(1, 12.0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port",
-                                "sample": "oracle port (C tree + torch-CPU net, batch-1 eval): 1 process, %.0f s of self-play at %d "
-                                          "sims/move (%d sims)" % (el, BUDGET, s)}
+        cores = usable_cores()
+        r_all = reference_sample(cores, REF_PLIES)
+        if r_all is not None:
+            r_one = reference_sample(1, 2)
+            line["cpu_baseline"] = {"value": r_all["sims_per_sec"], "unit": UNIT, "cores": r_all["cores"], "kind": "reference",
+                                    "sample": "the reference's own generate_data() (oracle/_ref byte code, torch-CPU stand-in for Keras, 1 thread "
+                                              "per worker): %d worker processes x 1 game cut after %d plies at %d sims/move = %d sims in %.1f s"
+                                              % (r_all["cores"], REF_PLIES, BUDGET, r_all["sims"], r_all["seconds"]),
+                                    "one_core": None if r_one is None else {"value": r_one["sims_per_sec"], "cores": 1, "sims": r_one["sims"],
+                                                                            "seconds": r_one["seconds"]}}
+        else:
+            from oracle import oracle as O
+            O.build()
+            v, c, s, el = cpu_port_sample(1, 12.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": c, "kind": "port",
+                                    "sample": "oracle port (C tree + torch-CPU net, batch-1 eval): 1 process, %.0f s of self-play at %d "
+                                              "sims/move (%d sims)" % (el, BUDGET, s)}
     emit(line)
 
 
@@ -380,6 +539,11 @@ def main():
     ap.add_argument("--slots", type=int, default=SLOTS)
     ap.add_argument("--rounds", type=int, default=ROUNDS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the generate_data() wall-clock measurement")
+    ap.add_argument("--no-eval-cache", action="store_true", help="evaluate every leaf (A/B of the evaluation cache)")
+    ap.add_argument("--preroll", type=int, default=PREROLL_ROUNDS)
+    ap.add_argument("--pipeline-games", type=int, default=SLOTS)
+    ap.add_argument("--pipeline-workers", type=int, default=32, help="NUM_CPUS of the generate_data() call (files written)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

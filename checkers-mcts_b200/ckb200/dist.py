@@ -38,6 +38,95 @@ def gather_records(records, rank, world, device=None, dst=0):
     return np.concatenate(parts) if parts else records[:0]
 
 
+def gather_packed(hdr, words, rank, world, device=None, dst=0):
+    """Packed records (``RECORD_HDR_DTYPE`` headers + uint32 child words, see ckb200.records.pack) of every rank on
+    ``dst``: exact-size point-to-point transfers (one grouped NCCL send/recv batch on GPUs, gloo send/recv in the CPU
+    tests) straight between the buffers that are handed in -- torch tensors (device-resident: no host bounce) or numpy
+    arrays.  No padding to the largest rank.  -> (hdr bytes tensor, words tensor, per-rank (n_hdr_bytes, n_words)) on
+    ``dst``, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cpu") if device is None else torch.device(device)
+
+    def as_tensor(a, np_dtype):
+        if isinstance(a, torch.Tensor):
+            return a.reshape(-1)
+        flat = np.ascontiguousarray(a).reshape(-1)
+        flat = flat.view(np_dtype) if flat.size else np.zeros(0, dtype=np_dtype)
+        return torch.from_numpy(flat.copy()).to(dev)
+
+    h = as_tensor(hdr, np.uint8)
+    w = as_tensor(words, np.int32)
+    mine = torch.tensor([h.numel(), w.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, mine)
+    sizes = [(int(t[0].item()), int(t[1].item())) for t in sizes]
+    if rank != dst:
+        ops = []
+        if h.numel():
+            ops.append(dist.P2POp(dist.isend, h, dst))
+        if w.numel():
+            ops.append(dist.P2POp(dist.isend, w, dst))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return None
+    H = torch.empty(sum(a for a, _ in sizes), dtype=torch.uint8, device=dev)
+    W = torch.empty(sum(b for _, b in sizes), dtype=torch.int32, device=dev)
+    ops, ho, wo = [], 0, 0
+    for r, (a, b) in enumerate(sizes):
+        if r == dst:
+            H[ho:ho + a] = h
+            W[wo:wo + b] = w
+        else:
+            if a:
+                ops.append(dist.P2POp(dist.irecv, H[ho:ho + a], r))
+            if b:
+                ops.append(dist.P2POp(dist.irecv, W[wo:wo + b], r))
+        ho += a
+        wo += b
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return H, W, sizes
+
+
+def gather_engine_records(engine, rank, world, device, dst=0, want_info=False):
+    """The iteration-end gather (the reference's Pool.map return + merge_data, training_pipeline.py:277-284, 323-332):
+    every rank packs the records of its finished games ON THE DEVICE into two torch buffers (ck_records_pack_device,
+    ~75 bytes per record instead of 372), ``dst`` receives them with exact-size NCCL point-to-point transfers and
+    unpacks once.  -> (RECORD_DTYPE array of all ranks ordered by rank on ``dst`` / None elsewhere, milliseconds), or with
+    ``want_info`` a dict(ms, bytes) in place of the milliseconds."""
+    import time
+    import torch
+    from . import records as R
+    from .lib_types import RECORD_HDR_DTYPE
+    dev = torch.device(device)
+    torch.cuda.synchronize(dev)
+    t0 = time.time()
+    n, nw = engine.records_packed_sizes()
+    h = torch.empty(max(n, 1) * RECORD_HDR_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    w = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+    if n:
+        engine.records_pack_device(h.data_ptr(), n, w.data_ptr(), max(nw, 1))
+    h, w = h[:n * RECORD_HDR_DTYPE.itemsize], w[:nw]
+    if world > 1:
+        got = gather_packed(h, w, rank, world, device=dev, dst=dst)
+    else:
+        got = (h, w, [(h.numel(), w.numel())])
+    out = None
+    nbytes = 0
+    if got is not None:
+        H, W, sizes = got
+        nbytes = H.numel() + 4 * W.numel()
+        hdr = H.cpu().numpy().view(RECORD_HDR_DTYPE)
+        words = W.cpu().numpy().view(np.uint32)
+        out = R.unpack(hdr, words)
+    torch.cuda.synchronize(dev)
+    ms = 1000.0 * (time.time() - t0)
+    return (out, dict(ms=ms, bytes=nbytes)) if want_info else (out, ms)
+
+
 def rank_world():
     """(rank, world, local_rank) of the default torch.distributed group; (0, 1, None) outside one"""
     import os

@@ -23,7 +23,7 @@ EVAL_KINDS = {"net": EVAL_NET, "uniform_zero": EVAL_UNIFORM_ZERO, "uniform_mater
 NET_IMPL_TC, NET_IMPL_SIMT = 0, 1
 ERR_NET_RANGE = 8
 
-from .lib_types import GAME_DTYPE, LEAF_DTYPE, POS_DTYPE, RECORD_DTYPE  # noqa: E402,F401
+from .lib_types import GAME_DTYPE, LEAF_DTYPE, POS_DTYPE, RECORD_DTYPE, RECORD_HDR_DTYPE  # noqa: E402,F401
 
 
 class EngineCfg(C.Structure):
@@ -79,6 +79,7 @@ def _load():
     L.ck_net_forward_planes.argtypes = [vp, vp, i64, vp, vp]
     L.ck_net_forward_logits.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     L.ck_net_range_status.argtypes = [vp]
+    L.ck_net_last_features.argtypes = [vp, i64, vp, vp]
     L.ck_movegen_csr.argtypes = [C.c_int, vp, i64, vp, i64, vp, vp, vp, vp]
     L.ck_movegen_csr_device.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, vp]
     L.ck_net_forward_device.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -99,7 +100,10 @@ def _load():
     L.ck_records_count.restype = i64
     L.ck_records_fetch.argtypes = [vp, vp, i64]
     L.ck_records_fetch_new.argtypes = [vp, vp, i64, vp, vp]
+    L.ck_records_pack_device.argtypes = [vp, vp, i64, vp, i64, vp, vp]
+    L.ck_records_fetch_packed.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     L.ck_engine_set_profile.argtypes = [vp, C.c_int]
+    L.ck_engine_set_budget.argtypes = [vp, i32]
     L.ck_tree_set_root.argtypes = [vp, vp, i32]
     L.ck_tree_search.argtypes = [vp, i32]
     L.ck_tree_root.argtypes = [vp, vp, vp, vp]
@@ -233,6 +237,13 @@ class Net(object):
         check(_lib.ck_net_forward_logits(self._h, _ptr(leaves), n, _ptr(policy), _ptr(value), _ptr(logits), _ptr(vpre)))
         return policy, value, logits, vpre
 
+    def last_features(self, n):
+        """tower outputs of the last tensor-core forward of n positions: (pflat [n,512], vconv [n,64])"""
+        pflat = np.empty((n, POLICY_SIZE), dtype=np.float32)
+        vconv = np.empty((n, 64), dtype=np.float32)
+        check(_lib.ck_net_last_features(self._h, n, _ptr(pflat), _ptr(vconv)))
+        return pflat, vconv
+
     def range_status(self):
         """raises CkError(CK_ERR_NET_RANGE) if an activation left the tensor-core path's fp16 range"""
         check(_lib.ck_net_range_status(self._h))
@@ -288,6 +299,10 @@ class Engine(object):
         self._nets[which] = net          # keep alive
         check(_lib.ck_engine_set_net(self._h, which, net._h))
 
+    def set_budget(self, budget):
+        check(_lib.ck_engine_set_budget(self._h, int(budget)))
+        self.cfg.budget = int(budget)
+
     def set_profile(self, on):
         check(_lib.ck_engine_set_profile(self._h, int(bool(on))))
 
@@ -324,6 +339,30 @@ class Engine(object):
         if n:
             check(_lib.ck_records_fetch(self._h, _ptr(out), len(out)))
         return out[:n]
+
+    def records_packed_sizes(self):
+        """(n_records, n_words) of the packed form of all finished games' records"""
+        n, w = C.c_int64(), C.c_int64()
+        check(_lib.ck_records_pack_device(self._h, None, 0, None, 0, C.byref(n), C.byref(w)))
+        return n.value, w.value
+
+    def records_pack_device(self, hdr_ptr, hdr_cap, words_ptr, word_cap):
+        """pack into caller-provided device buffers (raw pointers, e.g. torch tensors' data_ptr()); -> (n_records, n_words)"""
+        n, w = C.c_int64(), C.c_int64()
+        check(_lib.ck_records_pack_device(self._h, C.c_void_p(int(hdr_ptr)), int(hdr_cap), C.c_void_p(int(words_ptr)), int(word_cap),
+                                          C.byref(n), C.byref(w)))
+        return n.value, w.value
+
+    def records_packed(self):
+        """all finished games' records in packed form on the host: (RECORD_HDR_DTYPE array, uint32 child words);
+        ckb200.records.unpack turns them into RECORD_DTYPE"""
+        n, w = self.records_packed_sizes()
+        hdr = np.zeros(max(n, 1), dtype=RECORD_HDR_DTYPE)
+        words = np.zeros(max(w, 1), dtype=np.uint32)
+        if n:
+            a, b = C.c_int64(), C.c_int64()
+            check(_lib.ck_records_fetch_packed(self._h, _ptr(hdr), len(hdr), _ptr(words), len(words), C.byref(a), C.byref(b)))
+        return hdr[:n], words[:w]
 
     def records_new(self, buf):
         """records of games finished since the last call, written into ``buf`` (RECORD_DTYPE array);

@@ -9,6 +9,9 @@ RECORD_DTYPE = np.dtype([
     ("pos", POS_DTYPE), ("mask", "<u4", (8,)), ("plane5", "<i4"), ("n_children", "<i4"),
     ("action", "<u2", (MAX_CHILDREN,)), ("visits", "<u4", (MAX_CHILDREN,)), ("q", "<f4"), ("z", "<i4"),
     ("root_n", "<u4"), ("root_w", "<f4"), ("chosen", "<i4"), ("game", "<i4"), ("ply", "<i4")])
+RECORD_HDR_DTYPE = np.dtype([          # ck_record_hdr: packed record header, followed by one uint32 per child in the word stream
+    ("pos", POS_DTYPE), ("q", "<f4"), ("root_w", "<f4"), ("root_n", "<u4"), ("game", "<i4"), ("ply", "<u2"), ("chosen", "<i2"),
+    ("n_children", "u1"), ("plane5", "u1"), ("z", "i1"), ("flags", "u1")])
 GAME_DTYPE = np.dtype([
     ("game", "<i4"), ("outcome", "<i4"), ("move_count", "<i4"), ("terminated", "<i4"),
     ("n_records", "<i4"), ("reroot_misses", "<i4"), ("p1_net", "<i4"), ("reserved", "<i4"),

@@ -116,6 +116,65 @@ def training_batch(records):
     return x, [probs, v]
 
 
+# ---- packed wire format (ck_record_hdr + child words, include/ckb200.h) ------------------------------------------------
+def _mask_of_actions(rows, actions, n):
+    """legal-action planes 6..13 as square sets [n,8] from (record row, action id) pairs: plane = a >> 6, square of
+    (x, y) = ((a >> 3) & 7, a & 7) is s = 4x + (y >> 1)"""
+    mask = np.zeros((n, 8), dtype=np.uint32)
+    a = actions.astype(np.int64)
+    bit = (np.uint32(1) << (4 * ((a >> 3) & 7) + ((a & 7) >> 1)).astype(np.uint32)).astype(np.uint32)
+    np.bitwise_or.at(mask, (rows, a >> 6), bit)
+    return mask
+
+
+def pack(records):
+    """RECORD_DTYPE array -> (RECORD_HDR_DTYPE array, uint32 words): numpy twin of the device-side pack kernel"""
+    from .lib_types import RECORD_HDR_DTYPE
+    n = len(records)
+    hdr = np.zeros(n, dtype=RECORD_HDR_DTYPE)
+    for f in ("pos", "q", "root_w", "root_n", "game", "ply", "chosen", "n_children", "plane5", "z"):
+        hdr[f] = records[f]
+    nch = records["n_children"].astype(np.int64)
+    mf = (nch == 0) & (records["mask"] != 0).any(axis=1)
+    hdr["flags"] = mf.astype(np.uint8)
+    nw = nch + 8 * mf
+    offs = np.concatenate([[0], np.cumsum(nw)])
+    words = np.zeros(int(offs[-1]), dtype=np.uint32)
+    cols = np.arange(records["visits"].shape[1])[None, :]
+    live = cols < nch[:, None]
+    dst = (offs[:-1, None] + cols)[live]
+    words[dst] = (records["action"].astype(np.uint32)[live] << np.uint32(23)) | (records["visits"][live] & np.uint32(0x7FFFFF))
+    for i in np.nonzero(mf)[0]:
+        words[offs[i]:offs[i] + 8] = records["mask"][i]
+    return hdr, words
+
+
+def unpack(hdr, words):
+    """(headers, child words) -> RECORD_DTYPE array, bit-identical to what ck_records_fetch returns"""
+    from .lib_types import RECORD_DTYPE
+    n = len(hdr)
+    out = np.zeros(n, dtype=RECORD_DTYPE)
+    for f in ("pos", "q", "root_w", "root_n", "game", "ply", "chosen", "n_children", "plane5", "z"):
+        out[f] = hdr[f]
+    nch = hdr["n_children"].astype(np.int64)
+    mf = hdr["flags"].astype(bool) & (nch == 0)
+    nw = nch + 8 * mf
+    offs = np.concatenate([[0], np.cumsum(nw)])
+    if int(offs[-1]) != len(words):
+        raise ValueError("packed records: %d child words expected, %d present" % (int(offs[-1]), len(words)))
+    cols = np.arange(out["visits"].shape[1])[None, :]
+    live = cols < nch[:, None]
+    w = words[(offs[:-1, None] + cols)[live]]
+    rows = np.broadcast_to(np.arange(n)[:, None], live.shape)[live]
+    cc = np.broadcast_to(cols, live.shape)[live]
+    out["action"][rows, cc] = (w >> np.uint32(23)).astype(np.uint16)
+    out["visits"][rows, cc] = w & np.uint32(0x7FFFFF)
+    out["mask"] = _mask_of_actions(rows, w >> np.uint32(23), n)
+    for i in np.nonzero(mf)[0]:
+        out["mask"][i] = words[offs[i]:offs[i] + 8]
+    return out
+
+
 # ---- per-worker pickle files ------------------------------------------------------------------------
 def _save_one(args):
     records, filename, playouts = args

@@ -994,6 +994,66 @@ playout_eval_kernel(const ck_leaf *__restrict__ leaves, const int32_t *__restric
     value[row] = (float)st;
 }
 
+// ---- packed records (iteration-end gather) ------------------------------------------------------
+// A ck_record is 372 bytes, most of it empty child slots.  Packed form: a 40-byte header per record plus one word per
+// child (action << 23 | visits) -- about 75 bytes per record -- written game by game (local game order, plies in
+// order) straight from the engine's record store, so that the gather moves a fifth of the bytes and needs no host
+// bounce.  The legal-action planes of a searched position are exactly its children's actions and are rebuilt by the
+// receiver; a terminal record whose position still has legal moves (a draw by the 80-ply rule) appends its 8 mask words.
+__device__ __forceinline__ int packed_words(const ck_record &r, bool *mask_follows) {
+    const bool mf = r.n_children == 0 && (r.mask[0] | r.mask[1] | r.mask[2] | r.mask[3] | r.mask[4] | r.mask[5] | r.mask[6] | r.mask[7]) != 0u;
+    *mask_follows = mf;
+    return r.n_children + (mf ? 8 : 0);
+}
+
+// thread per game: records and child words of a finished game (0 / 0 otherwise)
+__global__ void pack_count_kernel(const EngineDev E, int64_t *__restrict__ counts) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.n_games) return;
+    const ck_game_result r = E.results[g];
+    int64_t nrec = 0, nw = 0;
+    if (r.game >= 0 && r.outcome >= 0) {
+        nrec = r.n_records;
+        const ck_record *rec = E.rec + (int64_t)g * E.max_rec;
+        for (int i = 0; i < r.n_records; ++i) { bool mf; nw += packed_words(rec[i], &mf); }
+    }
+    counts[2 * g] = nrec; counts[2 * g + 1] = nw;
+}
+
+// warp per game; offs[2g], offs[2g+1] = first header / first child word of game g
+__global__ void __launch_bounds__(128)
+pack_write_kernel(const EngineDev E, const int64_t *__restrict__ counts, const int64_t *__restrict__ offs,
+                  ck_record_hdr *__restrict__ hdr, uint32_t *__restrict__ words) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= E.n_games) return;
+    const int nrec = (int)counts[2 * g];
+    if (nrec == 0) return;
+    const ck_record *rec = E.rec + (int64_t)g * E.max_rec;
+    ck_record_hdr *h = hdr + offs[2 * g];
+    int64_t wbase = offs[2 * g + 1];
+    for (int r0 = 0; r0 < nrec; r0 += 32) {
+        const int i = r0 + lane;
+        bool mf = false;
+        const int nw = i < nrec ? packed_words(rec[i], &mf) : 0;
+        int incl = nw;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(CK_FULL, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(CK_FULL, incl, 31);
+        if (i < nrec) {
+            const ck_record &R = rec[i];
+            ck_record_hdr o;
+            o.pos = R.pos; o.q = R.q; o.root_w = R.root_w; o.root_n = R.root_n; o.game = R.game;
+            o.ply = (uint16_t)R.ply; o.chosen = (int16_t)R.chosen; o.n_children = (uint8_t)R.n_children;
+            o.plane5 = (uint8_t)R.plane5; o.z = (int8_t)R.z; o.flags = mf ? 1u : 0u;
+            h[i] = o;
+            uint32_t *w = words + wbase + (incl - nw);
+            for (int j = 0; j < R.n_children; ++j) w[j] = ((uint32_t)R.action[j] << 23) | (R.visits[j] & 0x7FFFFFu);
+            if (mf) for (int j = 0; j < 8; ++j) w[j] = R.mask[j];
+        }
+        wbase += total;
+    }
+}
+
 }  // namespace ck
 
 // =================================================================================================
@@ -1170,6 +1230,17 @@ int ck_engine_set_net(ck_engine *e, int which, ck_net *net) {
     if (net->device != e->dev.cfg.device) return fail(CK_ERR_ARG, "ck_engine_set_net: net lives on another device");
     e->net[which] = net;
     e->net_gen[which] = 0;              // (generations start at 1) the next run clears the evaluation cache
+    return CK_OK;
+}
+
+// BUDGET of the searches that start (or are under way) from now on; the trees already built are kept.  bench.py
+// uses it to desynchronise the slots with a cheap pre-roll before the timed region.
+int ck_engine_set_budget(ck_engine *e, int32_t budget) {
+    if (!e || budget < 1) return fail(CK_ERR_ARG, "ck_engine_set_budget: budget must be >= 1");
+    EngineDev &d = e->dev;
+    int64_t need = (int64_t)budget * CK_MAX_CHILDREN;       // room for a whole search in the worst case (see ck_engine_create)
+    d.compact_need = (int32_t)(need > d.cap / 2 ? d.cap / 2 : need);
+    d.cfg.budget = budget;
     return CK_OK;
 }
 
@@ -1480,6 +1551,63 @@ int ck_records_fetch_new(ck_engine *e, ck_record *out, int64_t cap, int64_t *n_o
     *n_out = k;
     if (n_games_out) *n_games_out = ng;
     return CK_OK;
+}
+
+// packed records of all finished games into caller-provided DEVICE buffers (NULL buffers: sizes only)
+int ck_records_pack_device(ck_engine *e, ck_record_hdr *d_hdr, int64_t hdr_cap, uint32_t *d_words, int64_t word_cap,
+                           int64_t *n_records, int64_t *n_words) {
+    if (!e || !e->begun || !n_records || !n_words) return fail(CK_ERR_ARG, "ck_records_pack_device: bad arguments");
+    if (!e->dev.cfg.keep_records) return fail(CK_ERR_STATE, "ck_records_pack_device: engine was created with keep_records = 0");
+    EngineDev &d = e->dev;
+    // a child word holds 23 bits of visits; visit counts are bounded by the simulations of all searches of a game
+    if ((int64_t)d.cfg.budget * d.max_rec >= (1 << 23)) return fail(CK_ERR_ARG, "ck_records_pack_device: BUDGET x plies exceeds the packed format's 23-bit visit counts; use ck_records_fetch");
+    DeviceGuard g(d.cfg.device);
+    const int64_t ng = e->n_games;
+    int64_t *d_counts = nullptr;
+    CK_CUDA(cudaMalloc(&d_counts, (size_t)ng * 4 * sizeof(int64_t)));           // counts, then offsets
+    int64_t *d_offs = d_counts + 2 * ng;
+    std::vector<int64_t> counts((size_t)2 * ng), offs((size_t)2 * ng);
+    pack_count_kernel<<<(unsigned)((ng + 127) / 128), 128, 0, e->stream>>>(d, d_counts);
+    cudaError_t ce = cudaMemcpyAsync(counts.data(), d_counts, (size_t)2 * ng * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    int64_t nr = 0, nw = 0;
+    for (int64_t i = 0; i < ng; ++i) { offs[2 * i] = nr; offs[2 * i + 1] = nw; nr += counts[2 * i]; nw += counts[2 * i + 1]; }
+    *n_records = nr; *n_words = nw;
+    int rc = CK_OK;
+    if (ce == cudaSuccess && d_hdr && d_words) {
+        if (nr > hdr_cap || nw > word_cap) rc = fail(CK_ERR_ARG, "ck_records_pack_device: buffers too small");
+        else if (nr > 0) {
+            ce = cudaMemcpyAsync(d_offs, offs.data(), (size_t)2 * ng * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream);
+            pack_write_kernel<<<(unsigned)((ng * 32 + 127) / 128), 128, 0, e->stream>>>(d, d_counts, d_offs, d_hdr, d_words);
+            if (ce == cudaSuccess) ce = cudaGetLastError();
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        }
+    }
+    cudaFree(d_counts);
+    if (ce != cudaSuccess) return fail(CK_ERR_CUDA, std::string("ck_records_pack_device: ") + cudaGetErrorString(ce));
+    return rc;
+}
+
+// the same into HOST buffers (a fifth of the bytes of ck_records_fetch over PCIe)
+int ck_records_fetch_packed(ck_engine *e, ck_record_hdr *hdr, int64_t hdr_cap, uint32_t *words, int64_t word_cap,
+                            int64_t *n_records, int64_t *n_words) {
+    int rc = ck_records_pack_device(e, nullptr, 0, nullptr, 0, n_records, n_words);
+    if (rc != CK_OK || !hdr || !words) return rc;
+    if (*n_records > hdr_cap || *n_words > word_cap) return fail(CK_ERR_ARG, "ck_records_fetch_packed: buffers too small");
+    if (*n_records == 0) return CK_OK;
+    DeviceGuard g(e->dev.cfg.device);
+    ck_record_hdr *d_hdr = nullptr;
+    uint32_t *d_words = nullptr;
+    CK_CUDA(cudaMalloc(&d_hdr, (size_t)*n_records * sizeof(ck_record_hdr)));
+    cudaError_t ce = cudaMalloc(&d_words, (size_t)(*n_words + 1) * sizeof(uint32_t));
+    if (ce == cudaSuccess) {
+        rc = ck_records_pack_device(e, d_hdr, *n_records, d_words, *n_words + 1, n_records, n_words);
+        if (rc == CK_OK) ce = cudaMemcpy(hdr, d_hdr, (size_t)*n_records * sizeof(ck_record_hdr), cudaMemcpyDeviceToHost);
+        if (rc == CK_OK && ce == cudaSuccess) ce = cudaMemcpy(words, d_words, (size_t)*n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_hdr); cudaFree(d_words);
+    if (ce != cudaSuccess) return fail(CK_ERR_CUDA, std::string("ck_records_fetch_packed: ") + cudaGetErrorString(ce));
+    return rc;
 }
 
 // ---- single-search API (slot 0) -----------------------------------------------------------

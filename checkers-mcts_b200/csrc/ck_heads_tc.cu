@@ -32,6 +32,13 @@ constexpr int kSmem = 2 * kChunkBytes + 64;
 constexpr float kActScale = 16.0f;
 constexpr size_t kPackBytes = (size_t)4 * 4 * kChunkBytes;   // [out quarter][k chunk][hi|lo][k/8][out 128][8]
 constexpr uint32_t kIdesc = make_idesc_f16(kM, kN);
+// The tensor pipe rounds its fp32 accumulator toward zero after every MMA, so a long accumulation chain loses about
+// half an ulp per instruction in one direction (measured on the reference's trained networks: logits off by 1e-5
+// relative with one 96-instruction chain).  Three accumulators keep the chains short where the values are large: the
+// hi*hi products of K chunks {0,1} and {2,3} (16 instructions each) and all hi*lo + lo*hi cross terms (2^-11 of the
+// magnitude, so their 64 roundings do not matter); the epilogue adds them in fp32 round-to-nearest.
+constexpr int kTmemCols = 512;                      // 3 x 128 used (allocations are powers of two)
+constexpr uint32_t kColMain0 = 0, kColMain1 = kN, kColCross = 2 * kN;
 
 __global__ void __launch_bounds__(kThreads, 1)
 heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int32_t *__restrict__ n_dev,
@@ -50,7 +57,7 @@ heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int3
     if (warp == 0) {
         if (lane == 0) { mbar_init(bar_b, 1); mbar_init(bar_mma, 1); mbar_init_fence(); }
         __syncwarp();
-        tmem_alloc<kN>(smem_u32(s_tmem));
+        tmem_alloc<kTmemCols>(smem_u32(s_tmem));
     }
     fence_proxy_async();
     tc_fence_before();
@@ -103,9 +110,9 @@ heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int3
                     const uint64_t a_lo = make_desc(a0 + kSplit + ks * 2 * (kM * 16), kM * 16, 128);
                     const uint64_t b_hi = make_desc(b0 + ks * 2 * (kN * 16), kN * 16, 128);
                     const uint64_t b_lo = make_desc(b0 + kSplit + ks * 2 * (kN * 16), kN * 16, 128);
-                    tc_mma_ss(tmem, a_hi, b_hi, kIdesc, (kc | ks) != 0 ? 1u : 0u);
-                    tc_mma_ss(tmem, a_hi, b_lo, kIdesc, 1u);
-                    tc_mma_ss(tmem, a_lo, b_hi, kIdesc, 1u);
+                    tc_mma_ss(tmem + ((kc >> 1) ? kColMain1 : kColMain0), a_hi, b_hi, kIdesc, ((kc & 1) | ks) != 0 ? 1u : 0u);
+                    tc_mma_ss(tmem + kColCross, a_hi, b_lo, kIdesc, (kc | ks) != 0 ? 1u : 0u);
+                    tc_mma_ss(tmem + kColCross, a_lo, b_hi, kIdesc, 1u);
                 }
                 tc_commit(bar_mma);
             }
@@ -123,8 +130,13 @@ heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int3
         float *out = logits + pos * 512 + nq * kN + half * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float v[16];
-            tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64 + q * 16), v);
+            float v[16], v1[16], vc[16];
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64 + q * 16);
+            tmem_ld16(taddr + kColMain0, v);
+            tmem_ld16(taddr + kColMain1, v1);
+            tmem_ld16(taddr + kColCross, vc);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (v[i] + v1[i]) + vc[i];
             if (pos < n) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
@@ -136,7 +148,7 @@ heads_dense_tc_kernel(const float *__restrict__ pflat, int64_t max_n, const int3
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<kN>(tmem);
+    if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
 struct FinishParams { int64_t val_d1_k, val_d1_b, val_d2_k, val_d2_b; };

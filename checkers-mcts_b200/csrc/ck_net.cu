@@ -431,6 +431,26 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
     return CK_OK;
 }
 
+// ck_net_set_weights* with the values the net already holds is a no-op: the packed tensor-core operands stay, and so
+// does weights_gen, i.e. evaluations cached by the engines that use this net remain valid
+__global__ void blob_differs_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, int64_t n, int32_t *flag) {
+    bool diff = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) diff |= a[i] != b[i];
+    if (diff) atomicExch(flag, 1);
+}
+
+static int net_same_weights(ck_net *net, const float *d_new, bool *same) {
+    *same = false;
+    if (!net->have_weights) return CK_OK;
+    int32_t *flag = net->d_range_flag + 1;
+    CK_CUDA(cudaMemset(flag, 0, sizeof(int32_t)));
+    blob_differs_kernel<<<296, 256>>>((const uint32_t *)net->d_blob, (const uint32_t *)d_new, CK_NET_PARAM_COUNT, flag);
+    int32_t h = 1;
+    CK_CUDA(cudaMemcpy(&h, flag, sizeof(h), cudaMemcpyDeviceToHost));
+    *same = h == 0;
+    return CK_OK;
+}
+
 int net_check_range(ck_net *net) {
     int32_t flag = 0;
     CK_CUDA(cudaMemcpy(&flag, net->d_range_flag, sizeof(flag), cudaMemcpyDeviceToHost));
@@ -452,8 +472,8 @@ ck_net *ck_net_create(int device) {
     ck_net *net = new ck_net();
     net->device = device;
     CK_CUDA_PTR(cudaMalloc(&net->d_blob, CK_NET_PARAM_COUNT * sizeof(float)));
-    CK_CUDA_PTR(cudaMalloc(&net->d_range_flag, sizeof(int32_t)));
-    CK_CUDA_PTR(cudaMemset(net->d_range_flag, 0, sizeof(int32_t)));
+    CK_CUDA_PTR(cudaMalloc(&net->d_range_flag, 2 * sizeof(int32_t)));      // [0] range flag, [1] scratch of net_same_weights
+    CK_CUDA_PTR(cudaMemset(net->d_range_flag, 0, 2 * sizeof(int32_t)));
     return net;
 }
 
@@ -462,7 +482,7 @@ void ck_net_destroy(ck_net *net) {
     DeviceGuard g(net->device);
     cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack); cudaFree(net->d_wts); cudaFree(net->d_hpack);
     cudaFree(net->d_act0); cudaFree(net->d_act1);
-    cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value); cudaFree(net->d_range_flag);
+    cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value); cudaFree(net->d_range_flag); cudaFree(net->d_stage);
     delete net;
 }
 
@@ -476,6 +496,17 @@ int ck_net_set_weights(ck_net *net, const float *blob, int64_t count) {
     if (!net || !blob || count != net_layout().total || count != CK_NET_PARAM_COUNT)
         return fail(CK_ERR_ARG, "ck_net_set_weights: expected " + std::to_string(CK_NET_PARAM_COUNT) + " floats");
     DeviceGuard g(net->device);
+    if (net->have_weights) {
+        // stage the upload and compare on the device: unchanged weights keep the packed operands (and cached evaluations)
+        if (!net->d_stage) CK_CUDA(cudaMalloc(&net->d_stage, CK_NET_PARAM_COUNT * sizeof(float)));
+        CK_CUDA(cudaMemcpy(net->d_stage, blob, count * sizeof(float), cudaMemcpyHostToDevice));
+        bool same = false;
+        int rc = net_same_weights(net, net->d_stage, &same);
+        if (rc != CK_OK) return rc;
+        if (same) return CK_OK;
+        CK_CUDA(cudaMemcpy(net->d_blob, net->d_stage, count * sizeof(float), cudaMemcpyDeviceToDevice));
+        return net_finish_weights(net);
+    }
     CK_CUDA(cudaMemcpy(net->d_blob, blob, count * sizeof(float), cudaMemcpyHostToDevice));
     return net_finish_weights(net);
 }
@@ -484,6 +515,10 @@ int ck_net_set_weights_device(ck_net *net, const float *d_blob, int64_t count) {
     if (!net || !d_blob || count != CK_NET_PARAM_COUNT)
         return fail(CK_ERR_ARG, "ck_net_set_weights_device: expected " + std::to_string(CK_NET_PARAM_COUNT) + " floats");
     DeviceGuard g(net->device);
+    bool same = false;
+    int rc = net_same_weights(net, d_blob, &same);
+    if (rc != CK_OK) return rc;
+    if (same) return CK_OK;
     CK_CUDA(cudaMemcpy(net->d_blob, d_blob, count * sizeof(float), cudaMemcpyDeviceToDevice));
     return net_finish_weights(net);
 }
@@ -535,6 +570,19 @@ int ck_net_forward_logits(ck_net *net, const ck_leaf *leaves, int64_t n, float *
     cudaFree(d_dbg);
     if (rc == CK_ERR_CUDA && ce != cudaSuccess) return fail(CK_ERR_CUDA, std::string("ck_net_forward_logits: ") + cudaGetErrorString(ce));
     return rc;
+}
+
+// debug / parity: what the tower handed to the heads in the most recent forward call of `n` positions on the
+// tensor-core path -- pflat [n,512] (policy conv1x1 + ReLU + BN, flattened (x,y,c)) and vconv [n,64]
+int ck_net_last_features(ck_net *net, int64_t n, float *pflat, float *vconv) {
+    if (!net || n <= 0) return fail(CK_ERR_ARG, "ck_net_last_features: bad arguments");
+    if (net->impl != CK_NET_IMPL_TC || (size_t)n * 1024 > net->act1_floats || (size_t)n * 64 > net->act0_floats)
+        return fail(CK_ERR_STATE, "ck_net_last_features: no tensor-core forward of that size has run on this net");
+    DeviceGuard g(net->device);
+    CK_CUDA(cudaDeviceSynchronize());
+    if (pflat) CK_CUDA(cudaMemcpy(pflat, net->d_act1, (size_t)n * 512 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (vconv) CK_CUDA(cudaMemcpy(vconv, net->d_act0, (size_t)n * 64 * sizeof(float), cudaMemcpyDeviceToHost));
+    return CK_OK;
 }
 
 int ck_net_range_status(ck_net *net) {

@@ -29,6 +29,7 @@ struct ck_net {
     bool have_weights = false;
     uint64_t weights_gen = 0;        // bumped by every ck_net_set_weights*: consumers that cache evaluations compare it
     float *d_blob = nullptr;         // Keras-ordered fp32 parameters
+    float *d_stage = nullptr;        // ck_net_set_weights: the upload is staged here and compared with d_blob first
     float *d_scale = nullptr;        // folded BN: per layer 128 scale + 128 shift (tower), heads after
     // tcgen05 tower operands (built by ck_net_tc.cu)
     void *d_wpack = nullptr;         // split-fp16 weights in UMMA core-matrix order

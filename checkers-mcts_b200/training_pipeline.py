@@ -226,8 +226,11 @@ class generate_Checkers_data(object):
         self.device = selfplay_kwargs.get('DEVICE', 0)
         self.max_slots = selfplay_kwargs.get('MAX_CONCURRENT_GAMES', 4096)
         self.seed = selfplay_kwargs.get('SEED')
+        # under torchrun the games normally shard over the ranks; SINGLE_PROCESS keeps this call local to its process
+        self.single_process = bool(selfplay_kwargs.get('SINGLE_PROCESS', False))
         self.mcts_kwargs = mcts_kwargs
         self.stats = None
+        self.n_records, self.host_seconds = 0, 0.0
 
     def generate_data(self):
         """plays NUM_SELFPLAY_GAMES x NUM_CPUS games on the GPU; returns the list of pickle files,
@@ -239,7 +242,11 @@ class generate_Checkers_data(object):
         # under torchrun (one process per GPU) the games shard by index over the ranks, game g on rank g mod world,
         # every rank plays its share with the same seed (a game's random stream depends on its global index only)
         # and rank 0 pools the records: the files are the same as from a single process
-        rank, world, device, seed = _dist_setup(self.device, self.seed)
+        if self.single_process:
+            rank, world, device = 0, 1, self.device
+            seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little") >> 1
+        else:
+            rank, world, device, seed = _dist_setup(self.device, self.seed)
         spec = self.mcts_kwargs.get('PLAYOUT_EVALUATOR', 'rollout') if playouts else load_blob(self.nn_fn)
         base, stride, n_local = _D.shard(total, rank, world)
         recs, games = _np_empty(_L.RECORD_DTYPE), _np_empty(_L.GAME_DTYPE)
@@ -251,16 +258,23 @@ class generate_Checkers_data(object):
             try:
                 net = _attach(eng, 0, spec, device)
                 self.stats = eng.selfplay(n_local)
-                recs, games = eng.records(), eng.games()
+                games = eng.games()
+                if world > 1:                             # packed on the device, exact-size NCCL transfers to rank 0
+                    recs, _ms = _D.gather_engine_records(eng, rank, world, "cuda:%d" % device)
+                else:
+                    recs = _R.unpack(*eng.records_packed())     # a fifth of the bytes of the full records over PCIe
             finally:                                      # device memory goes back also when a run fails
                 eng.close()
                 if net is not None:
                     net.close()
+        elif world > 1:
+            raise ValueError('NUM_SELFPLAY_GAMES x NUM_CPUS must be at least the number of ranks')
         if world > 1:
-            recs = _D.gather_records(recs, rank, world, device="cuda:%d" % device)
             games = _D.gather_records(games, rank, world, device="cuda:%d" % device)
             if rank != 0:
                 return []
+        import time as _time
+        _t_host = _time.time()
         recs = recs[np.argsort(recs["game"], kind="stable")]       # game by game, plies in order
         games = games[np.argsort(games["game"], kind="stable")]
         names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}
@@ -272,6 +286,8 @@ class generate_Checkers_data(object):
         bounds = np.searchsorted(recs["game"], np.arange(self.num_cpus + 1) * self.NUM_SELFPLAY_GAMES)
         jobs = [(recs[bounds[p]:bounds[p + 1]], self._filename(self.TRAINING_ITERATION, timestamp, p)) for p in range(self.num_cpus)]
         filenames = _R.save_reference_pickles(jobs, playouts, workers=selfplay_workers(self.num_cpus))
+        self.n_records = int(len(recs))
+        self.host_seconds = _time.time() - _t_host        # sorting, conversion to the reference's lists, pickling
         return filenames if self.num_cpus > 1 else filenames[0]
 
     @staticmethod

@@ -107,6 +107,10 @@ int ck_net_forward(ck_net *, const ck_leaf *leaves, int64_t n, float *policy, fl
 /* the same plus what north_star's 1e-5 contract is stated on: the policy logits [n,512] (input of the Dense softmax,
  * training_pipeline.py:97-100) and the value head's pre-tanh output [n] (:111-112).  Any output pointer may be NULL. */
 int ck_net_forward_logits(ck_net *, const ck_leaf *leaves, int64_t n, float *policy, float *value, float *logits, float *value_pre);
+/* debug / parity: the tower's outputs of the most recent tensor-core forward call of n positions (its batch must have
+ * been exactly n): pflat [n,512] = policy conv1x1 + ReLU + BN flattened in (x,y,c) order (training_pipeline.py:89-97),
+ * vconv [n,64] = value conv1x1 + ReLU + BN (:102-105).  Not valid with CK_TOWER=ss. */
+int ck_net_last_features(ck_net *, int64_t n, float *pflat, float *vconv);
 /* The tensor-core path keeps activations as split fp16 scaled by 2^4: a BatchNorm output with |a| >= 4094 does not
  * fit.  The kernels flag it; the host entry points above return CK_ERR_NET_RANGE, the engine reports it from
  * ck_engine_run, and after ck_net_forward_device the caller asks here (synchronises the device). */
@@ -177,6 +181,22 @@ typedef struct {
     int32_t  ply;             /* index of the record inside its game */
 } ck_record;
 
+/* Packed record (the wire format of the iteration-end gather, training_pipeline.py:277-284,326-329): a fixed header
+ * plus one 32-bit word per child, action id << 23 | visits, in node.children order.  The legal-action planes of a
+ * searched position are its children's actions; flags bit 0: a terminal record (n_children = 0) whose position still has
+ * legal moves (draw by the 80-ply rule) is followed by its 8 mask words instead. */
+typedef struct {
+    ck_pos   pos;
+    float    q, root_w;
+    uint32_t root_n;
+    int32_t  game;
+    uint16_t ply;
+    int16_t  chosen;
+    uint8_t  n_children, plane5;
+    int8_t   z;
+    uint8_t  flags;
+} ck_record_hdr;             /* 40 bytes */
+
 typedef struct {
     int32_t game;             /* global game id */
     int32_t outcome;          /* CK_* (adjudicated when terminated) */
@@ -221,6 +241,16 @@ int64_t ck_records_count(ck_engine *);
 int ck_records_fetch(ck_engine *, ck_record *out, int64_t cap);
 /* records of the games that finished since the previous call; *n_out records, *n_games_out games */
 int ck_records_fetch_new(ck_engine *, ck_record *out, int64_t cap, int64_t *n_out, int64_t *n_games_out);
+/* change BUDGET for the searches that start or are under way from the next ck_engine_run on (MCTS.computational_budget,
+ * MCTS.py:188-201, reads the class attribute at every check, so the reference can be re-budgeted between moves too) */
+int ck_engine_set_budget(ck_engine *, int32_t budget);
+/* records of all finished games, packed (ck_record_hdr + child words), game by game in local game order, written into
+ * caller-provided DEVICE buffers (e.g. torch tensors that a NCCL send reads directly).  With d_hdr = d_words = NULL only
+ * the sizes are returned.  ck_records_fetch_packed: the same into host buffers. */
+int ck_records_pack_device(ck_engine *, ck_record_hdr *d_hdr, int64_t hdr_cap, uint32_t *d_words, int64_t word_cap,
+                           int64_t *n_records, int64_t *n_words);
+int ck_records_fetch_packed(ck_engine *, ck_record_hdr *hdr, int64_t hdr_cap, uint32_t *words, int64_t word_cap,
+                            int64_t *n_records, int64_t *n_words);
 /* time the evaluator separately inside ck_engine_run (adds two events per step) */
 int ck_engine_set_profile(ck_engine *, int on);
 

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 BN_EPS = 1e-3
 
 
-def forward(params, x, dtype=torch.float64, pre_activation=False):
+def forward(params, x, dtype=torch.float64, pre_activation=False, features=False):
     """params: dict from ckb200.net.unpack; x: [n,8,8,14] channels-last -> (policy [n,512], value [n]);
     with ``pre_activation`` also the policy logits [n,512] (before the softmax) and the value head's
     pre-tanh output [n] -- the quantities north_star's 1e-5 contract is stated on."""
@@ -37,13 +37,17 @@ def forward(params, x, dtype=torch.float64, pre_activation=False):
         h = conv(h, "conv%d" % i)
     p = conv(conv(h, "policy_conv1"), "policy_conv2")
     p = p.permute(0, 2, 3, 1).reshape(len(x), 512)                 # Flatten over (x, y, c)
+    pflat = p
     logits = p @ t(params["policy_head/kernel"]) + t(params["policy_head/bias"])
     p = torch.softmax(logits, dim=1)
     v = conv(h, "value_conv1").permute(0, 2, 3, 1).reshape(len(x), 64)
+    vconv = v
     v = F.relu(v @ t(params["value_dense1/kernel"]) + t(params["value_dense1/bias"]))
     v = bn(v, "value_dense1", 1)
     vpre = v @ t(params["value_head/kernel"]) + t(params["value_head/bias"])
     v = torch.tanh(vpre)
+    if features:        # also what the tower kernels hand to the heads: flattened policy features and the value conv output
+        return p.numpy(), v.reshape(-1).numpy(), logits.numpy(), vpre.reshape(-1).numpy(), pflat.numpy(), vconv.numpy()
     if pre_activation:
         return p.numpy(), v.reshape(-1).numpy(), logits.numpy(), vpre.reshape(-1).numpy()
     return p.numpy(), v.reshape(-1).numpy()

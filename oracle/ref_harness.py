@@ -18,6 +18,7 @@ import sys
 import types
 
 REFERENCE_DIR = os.environ.get("CK_REFERENCE_DIR", "/root/reference")
+COMPILED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # built by oracle/build_ref.py
 
 
 def reference_available():
@@ -77,20 +78,30 @@ _REF_MODULE_NAMES = ("Checkers", "MCTS", "training_pipeline", "TicTacToe",
                      "CLR", "CLR.clr_callback", "LRFinder", "LRFinder.keras_callback")
 
 
+def compiled_reference_available():
+    """the reference's own byte code under oracle/_ref (oracle/build_ref.py): what travels to the GPU box"""
+    from . import build_ref
+    return build_ref.available()
+
+
 @contextlib.contextmanager
-def reference_modules(with_pipeline=False):
+def reference_modules(with_pipeline=False, compiled=False):
     """Context manager yielding a namespace with the reference's own modules.
+    ``compiled``: import the byte-compiled copy in oracle/_ref instead of the source tree (bench.py's CPU arm).
 
     The repo ships drop-in modules with the same names (``Checkers``, ``MCTS``,
     ``training_pipeline``); to keep the two apart the reference copies are
     imported under a temporary ``sys.path``/``sys.modules`` and removed again on
     exit, and the caller keeps the module objects.
     """
-    if not reference_available():
+    ref_dir = COMPILED_DIR if compiled else REFERENCE_DIR
+    if compiled and not compiled_reference_available():
+        raise RuntimeError("compiled reference not built (python oracle/build_ref.py where /root/reference is mounted)")
+    if not compiled and not reference_available():
         raise RuntimeError("reference tree not mounted at %s" % REFERENCE_DIR)
     saved = {n: sys.modules.pop(n) for n in _REF_MODULE_NAMES if n in sys.modules}
     saved_path = list(sys.path)
-    sys.path.insert(0, REFERENCE_DIR)
+    sys.path.insert(0, ref_dir)
     try:
         ns = types.SimpleNamespace()
         ns.Checkers = importlib.import_module("Checkers")
@@ -98,7 +109,7 @@ def reference_modules(with_pipeline=False):
         if with_pipeline:
             install_stubs()
             ns.training_pipeline = importlib.import_module("training_pipeline")
-        assert os.path.dirname(ns.Checkers.__file__) == REFERENCE_DIR
+        assert os.path.dirname(ns.Checkers.__file__) == ref_dir
         yield ns
     finally:
         sys.path[:] = saved_path

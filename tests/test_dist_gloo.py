@@ -24,6 +24,25 @@ def _worker(rank, world, port, q):
         for k in range(3):
             recs[i * 3 + k] = (base + i * stride, k, rank + 0.5, [rank, i, k, 7, 9])
     out = D.gather_records(recs, rank, world)
+    # packed records: exact-size point-to-point transfers, ragged sizes (rank 1 sends nothing at all in the second call)
+    from ckb200 import records as R
+    from ckb200.lib_types import RECORD_DTYPE
+    full = np.zeros(n_local * 2, dtype=RECORD_DTYPE)
+    for i in range(len(full)):
+        full[i]["game"], full[i]["ply"], full[i]["n_children"] = base + (i // 2) * stride, i % 2, 3
+        full[i]["action"][:3], full[i]["visits"][:3] = (149, 151, 300 + rank), (5 + i, 7, 9)
+        full[i]["pos"] = (0xFFF, 0xFFF00000, 0, rank)
+    full["mask"] = R.unpack(*R.pack(full))["mask"]
+    for send in (full, full[:0] if rank == 1 else full):
+        h, w = R.pack(send)
+        got = D.gather_packed(h, w, rank, world)
+        if rank == 0:
+            H, W, sizes = got
+            back = R.unpack(H.numpy().view(h.dtype), W.numpy().view(np.uint32))
+            assert back[:len(send)].tobytes() == send.tobytes() and sizes[0] == (h.nbytes, len(w))
+            q.put(("packed", len(back)))
+        else:
+            assert got is None
     # iteration start: the weights and the seed of rank 0 reach every rank
     assert D.rank_world()[:2] == (rank, world)
     blob = D.broadcast_weights(np.arange(1000, dtype=np.float32) * 0.5 if rank == 0 else None, rank, world)
@@ -55,7 +74,10 @@ def test_shard_and_gather_two_ranks():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=120) for _ in range(4)]
+    packed = sorted(r[1] for r in res if r[0] == "packed")
+    assert packed == [12, 22]                         # rank 0: 6 games x 2 records; rank 1: 5 games x 2 (then nothing)
+    res = [r for r in res if r[0] != "packed"]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -357,6 +357,46 @@ def test_eval_cache_with_network_and_weight_change(lib):
     net.close()
 
 
+def test_packed_records_equal_full_records(lib):
+    """device-side packing (ck_records_pack_device / ck_records_fetch_packed: 40-byte headers + one word per child) loses
+    nothing: unpacked on the host it is bit-identical to ck_records_fetch, also with unfinished games in the store, and
+    equals the numpy twin of the pack kernel"""
+    from ckb200 import records as R
+    eng = lib.Engine(lib.make_cfg(n_slots=9, budget=40, training=True, terminate_cnt=0, evaluator="hash_salted", epsilon=0.25,
+                                  alpha=1.0, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=3, max_plies=600))
+    eng.begin(30)
+    eng.run(1500)                                     # some games finished, some in flight, some not started
+    full = eng.records()
+    hdr, words = eng.records_packed()
+    assert 0 < len(full) == len(hdr) and hdr.dtype.itemsize == 40
+    assert R.unpack(hdr, words).tobytes() == full.tobytes()
+    h2, w2 = R.pack(full)
+    assert h2.tobytes() == hdr.tobytes() and w2.tobytes() == words.tobytes()
+    assert hdr.nbytes + words.nbytes < full.nbytes / 4
+    eng.run(0)                                        # to the end
+    full = eng.records()
+    assert R.unpack(*eng.records_packed()).tobytes() == full.tobytes() and eng.games_finished() == 30
+    eng.close()
+
+
+def test_set_budget_between_runs(lib):
+    """ck_engine_set_budget: searches that start after the call use the new BUDGET (bench.py's pre-roll); every record's
+    visit counts tell which budget its search ran with"""
+    eng = lib.Engine(lib.make_cfg(n_slots=4, budget=50, training=True, terminate_cnt=30, evaluator="hash_salted"))
+    eng.begin(4)
+    eng.set_budget(5)
+    eng.run(40)
+    eng.set_budget(50)
+    eng.run(0)
+    recs = eng.records()
+    searched = recs[recs["n_children"] > 0]
+    new = searched["root_n"].astype(np.int64) - 1
+    assert len(searched) == 4 * 30
+    small, large = searched[searched["ply"] < 3], searched[searched["ply"] > 25]
+    assert (small["visits"].sum(axis=1) <= 5 + 5).all() and (large["visits"].sum(axis=1) >= 50).all() and (new >= 5).all()
+    eng.close()
+
+
 def test_uct_first_search_golden_and_midgame_vs_oracle(lib):
     """NEURAL_NET=False tree policy (MCTS.py:78-89,113-115): one child per visit, UCT in float64, one playout
     per simulation.  With hashed playouts the whole search is deterministic: the reference's own first search

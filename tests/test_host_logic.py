@@ -252,3 +252,35 @@ def test_play_checkers_move_listing_and_record_q():
     rec["root_n"], rec["root_w"], rec["q"] = 150, -7.0, np.float32(7.0) / np.float32(150.0)     # flipped to the root player's view
     assert R.to_reference(rec, playouts=True)[2] == 7 / 150 and type(R.to_reference(rec, playouts=True)[2]) is float
     assert R.to_reference(rec)[2] == np.float32(7.0) / np.float32(150.0)
+
+
+def test_packed_records_round_trip():
+    """ckb200.records.pack / unpack (numpy twins of the device-side pack kernel and of what rank 0 does after the
+    gather): bit-identical round trip on real game records, including a terminal record that carries its legal-action
+    planes (a draw by the 80-ply rule still has legal moves, Checkers.py:344-360)"""
+    from ckb200 import lib_types as T
+    from ckb200 import records as R
+    recs = []
+    for g in range(4):
+        gm = O.Game(O.make_cfg(budget=24, training=True, terminate_cnt=0 if g % 2 else 60, epsilon=0.25, tau=1.0, tau_decay=0.1,
+                               tau_decay_delay=10, seed=g), "hash_salted", None, salt=g)
+        gm.play()
+        recs.append(T.records_from_dicts(gm.records(), game=g))
+        gm.close()
+    recs = np.concatenate(recs)
+    draw = np.zeros(1, dtype=T.RECORD_DTYPE)                       # synthetic draw-terminal record: n_children 0, mask set
+    draw["pos"] = (0x00000001, 0x80000000, 0x80000001, 1 | (79 << 1) | (200 << 18))
+    draw["mask"][0] = (1, 0, 0, 0, 0, 0, 0, 0)
+    draw["plane5"], draw["chosen"], draw["game"], draw["ply"], draw["q"] = 80, -1, 9, 120, 0.0
+    recs = np.concatenate([recs[:7], draw, recs[7:]])
+    hdr, words = R.pack(recs)
+    assert hdr.dtype.itemsize == 40 and int(hdr["flags"].sum()) == 1
+    assert len(words) == int(recs["n_children"].sum()) + 8
+    back = R.unpack(hdr, words)
+    assert back.tobytes() == recs.tobytes()
+    assert hdr.nbytes + words.nbytes < recs.nbytes / 4
+    try:
+        R.unpack(hdr, words[:-1])
+        raise AssertionError("truncated word stream accepted")
+    except ValueError:
+        pass
