@@ -8,9 +8,9 @@ Workload (BASELINE.json configs[1]): 4096 concurrent self-play games per GPU, 40
 Dirichlet(alpha=1, eps=0.25) at every node, tau=1 with decay, TERMINATE_CNT=200, random-init network (seed 0); slots
 are refilled when their game ends.  One "step" = 400 lock-step rounds (tree kernel + batched network evaluation).
 
-Steady state: before the warm-up the slots are desynchronised by an untimed pre-roll at a tiny budget (games end and
-restart at scattered times), so the timed region sees games at every stage, finishing games included, instead of 4096
-openings in lock step.  Then 2K steps alternate:
+Steady state: the slots are desynchronised by a warm start (the first game of slot i plays its first hash(i) mod 140 plies
+at 8 sims/move, everything after that at 400) and an untimed pre-roll that takes every slot past those plies, so the
+timed region sees full-budget games at every stage, finishing games included, instead of 4096 openings in lock step.  Then 2K steps alternate:
   even steps -> `value`: simulations / device time (CUDA events on the engine's stream), inputs resident in HBM;
   odd steps  -> `e2e`: the same loop through the host-buffer C ABI, wall clock: the weight blob goes up from pinned host
                 memory (H2D), the step runs, the finished games' records and results come back (D2H).
@@ -40,9 +40,10 @@ UNIT = "sims/s"
 SLOTS = 4096
 BUDGET = 400
 ROUNDS_PER_STEP = 400
-PREROLL_BUDGET = 8            # sims/move of the untimed pre-roll that desynchronises the slots
-PREROLL_ROUNDS = 2400         # ~3 game lengths at that budget
-REF_PLIES = 4                 # plies per game of a reference-arm sample (the reference's TERMINATE_CNT knob)
+PREROLL_BUDGET = 8            # sims/move of the opening plies a slot's first game plays before full-budget play (warm start)
+PREROLL_PLIES = 140           # slot i does that for hash(i) mod 140 plies: stages spread over a typical game length
+PREROLL_ROUNDS = 1200         # untimed rounds that take every slot past its warm-start plies
+REF_PLIES = 2                 # plies per game of a reference-arm sample (the reference's TERMINATE_CNT knob)
 TOWER_FLOP_PER_POS = 2 * (9 * 14 * 128 * 64 + 7 * 9 * 128 * 128 * 64 + 128 * 8 * 64)   # 134,316,032: the eight 3x3 convs + the policy conv1x1 the tower kernel evaluates
 NET_FLOP_PER_POS = 134865024                                               # SURVEY 8(d), whole network
 MCTS = dict(uct_c=4.0, training=True, alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10,
@@ -335,7 +336,8 @@ def run_ours(args, rank, world, local_rank):
     base, stride, _n = D.shard(args.slots * world, rank, world)          # game g -> rank g mod world
     cfg = L.make_cfg(n_slots=args.slots, budget=BUDGET, device=dev, evaluator="net", keep_records=True,
                      seed=20261017, game_id_base=base, game_id_stride=stride,
-                     eval_cache_entries=-1 if args.no_eval_cache else 0, **MCTS)
+                     eval_cache_entries=-1 if args.no_eval_cache else 0,
+                     stagger_budget=PREROLL_BUDGET if args.preroll > 0 else 0, stagger_plies=PREROLL_PLIES if args.preroll > 0 else 0, **MCTS)
     eng = L.Engine(cfg)
     eng.set_net(0, net)
     n_games = args.slots * 16                    # staged games: enough refills for the pre-roll and any bench length
@@ -350,10 +352,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- untimed: desynchronise the slots (pre-roll at a tiny budget), then warm up at the real one ----------
     pre = dict(rounds=0, games=0, moves=0)
     if args.preroll > 0:
-        eng.set_budget(PREROLL_BUDGET)
         st = eng.run(args.preroll)
         pre = dict(rounds=int(st["steps"]), games=int(st["games_finished"]), moves=int(st["moves"]))
-        eng.set_budget(BUDGET)
         eng.records_new(rec_buf)                  # the pre-roll's records are not the bench's
     for _ in range(args.warmup):
         eng.run(args.rounds)
@@ -381,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
         nrec, ngames = eng.records_new(rec_buf)                             # D2H: this step's results
         torch.cuda.synchronize()
         e["ms"] += 1000.0 * (time.time() - s0)
-        e["sims"] += st["sims"]; e["launches"] += st["kernel_launches"]; e["games"] += ngames; e["records"] += nrec
+        e["sims"] += st["sims"]; e["launches"] += st["kernel_launches"]; e["games"] += st["games_finished"]; e["records"] += nrec
         e["h2d"] += blob.nbytes
         e["d2h"] += nrec * L.RECORD_DTYPE.itemsize + n_games * L.GAME_DTYPE.itemsize
     barrier()
@@ -431,9 +431,10 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic", "config": workload_config(world)}
     line["config"]["net_impl"] = args.net_impl
     line["config"]["eval_cache"] = "off" if args.no_eval_cache else "on (per-slot, 4096 entries)"
-    line["config"]["steady_state"] = ("untimed pre-roll of %d rounds at %d sims/move desynchronises the slots (%d games finished and were "
-                                      "replaced, %d moves), then %d warm-up steps at %d sims/move" %
-                                      (pre["rounds"], PREROLL_BUDGET, pre["games"], pre["moves"], args.warmup, BUDGET))
+    line["config"]["steady_state"] = ("warm start: the first game of slot i plays its first hash(i) mod %d plies at %d sims/move and everything "
+                                      "after that at %d, so slots reach full-budget play at scattered game stages; untimed pre-roll of %d rounds "
+                                      "(%d moves, %d games ended), then %d warm-up steps" %
+                                      (PREROLL_PLIES, PREROLL_BUDGET, BUDGET, pre["rounds"], pre["moves"], pre["games"], args.warmup))
     line["wall_s"] = wall
     line["nn_evals_per_sec"] = (evals - hits) / (gpu_ms / 1000.0)
     line["expansions_per_sec"] = evals / (gpu_ms / 1000.0)
@@ -492,7 +493,7 @@ def run_ours(args, rank, world, local_rank):
         cores = usable_cores()
         r_all = reference_sample(cores, REF_PLIES)
         if r_all is not None:
-            r_one = reference_sample(1, 2)
+            r_one = reference_sample(1, 1)
             line["cpu_baseline"] = {"value": r_all["sims_per_sec"], "unit": UNIT, "cores": r_all["cores"], "kind": "reference",
                                     "sample": "the reference's own generate_data() (oracle/_ref byte code, torch-CPU stand-in for Keras, 1 thread "
                                               "per worker): %d worker processes x 1 game cut after %d plies at %d sims/move = %d sims in %.1f s"

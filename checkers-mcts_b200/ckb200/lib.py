@@ -35,7 +35,7 @@ class EngineCfg(C.Structure):
         ("evaluator", C.c_int32), ("evaluator_p2", C.c_int32), ("arena", C.c_int32), ("keep_records", C.c_int32),
         ("reference_tau_quirk", C.c_int32), ("game_id_base", C.c_int32), ("game_id_stride", C.c_int32),
         ("max_terminal_sims_per_step", C.c_int32), ("compact_always", C.c_int32), ("eval_cache_entries", C.c_int32),
-        ("max_chain_per_step", C.c_int32), ("reserved0", C.c_int32)]
+        ("max_chain_per_step", C.c_int32), ("stagger_budget", C.c_int32), ("stagger_plies", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class RunStats(C.Structure):
@@ -274,7 +274,7 @@ def make_cfg(n_slots, budget, device=0, uct_c=4.0, training=False, alpha=1.0, ep
              tau_decay=0.0, tau_decay_delay=0, terminate_cnt=0, seed=1, evaluator="net", evaluator_p2=None,
              arena=False, keep_records=True, pool_cap=0, max_plies=0, reference_tau_quirk=False,
              game_id_base=0, game_id_stride=1, max_terminal_sims_per_step=0, compact_always=False,
-             eval_cache_entries=0, max_chain_per_step=0):
+             eval_cache_entries=0, max_chain_per_step=0, stagger_budget=0, stagger_plies=0):
     ev = EVAL_KINDS[evaluator] if isinstance(evaluator, str) else int(evaluator)
     ev2 = -1 if evaluator_p2 is None else (EVAL_KINDS[evaluator_p2] if isinstance(evaluator_p2, str) else int(evaluator_p2))
     return EngineCfg(device=device, n_slots=n_slots, pool_cap=pool_cap, max_plies=max_plies, budget=budget,
@@ -284,7 +284,8 @@ def make_cfg(n_slots, budget, device=0, uct_c=4.0, training=False, alpha=1.0, ep
                      reference_tau_quirk=int(bool(reference_tau_quirk)), game_id_base=game_id_base,
                      game_id_stride=game_id_stride, max_terminal_sims_per_step=max_terminal_sims_per_step,
                      compact_always=int(bool(compact_always)), eval_cache_entries=int(eval_cache_entries),
-                     max_chain_per_step=int(max_chain_per_step), reserved0=0)
+                     max_chain_per_step=int(max_chain_per_step), stagger_budget=int(stagger_budget),
+                     stagger_plies=int(stagger_plies), reserved0=0)
 
 
 class Engine(object):

@@ -46,7 +46,7 @@ struct Slot {
     int32_t buf[2], scratch;
     int32_t root[2], alloc[2], best[2], exists[2];
     int32_t nrec, misses, search_id, manual, manual_target;
-    int32_t pad;
+    int32_t stagger_until;   // plies of this game that are searched with cfg.stagger_budget (warm start, first game of a slot only)
     double tau;
     unsigned long long tot_sims, tot_evals;      // monotonic per slot; per-game totals are deltas
     unsigned long long g_sims0, g_evals0;
@@ -687,6 +687,10 @@ __device__ void init_game(const WarpCtx &c, int local_game) {
         S.buf[0] = 0; S.buf[1] = 1; S.scratch = 2;
         S.exists[0] = S.exists[1] = 0;
         S.nrec = 0; S.misses = 0; S.search_id = 0; S.g_sims0 = S.tot_sims; S.g_evals0 = S.tot_evals;
+        // warm start (benchmarks): the first game of a slot plays a slot-specific number of opening plies at a small budget,
+        // so that the slots reach full-budget play at different stages of their games instead of in lock step
+        S.stagger_until = (c.E.cfg.stagger_plies > 0 && S.tot_sims == 0)
+                              ? (int32_t)(mix32((uint32_t)c.slot * 0x9E3779B1u ^ (uint32_t)c.E.cfg.seed) % (uint32_t)c.E.cfg.stagger_plies) : 0;
         if (!c.E.cfg.reference_tau_quirk || S.tau < -1e300) S.tau = c.E.cfg.tau;
         c.hist[0] = start_position();
     }
@@ -870,7 +874,7 @@ tree_step_kernel(const EngineDev E) {
     const int max_term = E.max_term, max_chain = E.max_chain;
     while (live && S.phase != PH_HALT) {
         if (S.phase == PH_NEED_ROOT) setup_root(c);
-        const int target = S.manual ? S.manual_target : E.cfg.budget;
+        const int target = S.manual ? S.manual_target : (S.move_count < S.stagger_until ? E.cfg.stagger_budget : E.cfg.budget);
         if (S.sims_done >= target) {                     // MCTS.computational_budget (MCTS.py:196-198)
             if (S.manual) { __syncwarp(); if (lane == 0) S.phase = PH_HALT; __syncwarp(); break; }
             if (!play_move(c)) { live = false; break; }
@@ -1112,6 +1116,7 @@ extern "C" {
 
 ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     if (!cfg || cfg->n_slots < 1 || cfg->budget < 1) { fail(CK_ERR_ARG, "ck_engine_create: n_slots and budget must be >= 1"); return nullptr; }
+    if (cfg->stagger_plies > 0 && cfg->stagger_budget < 1) { fail(CK_ERR_ARG, "ck_engine_create: stagger_plies needs stagger_budget >= 1"); return nullptr; }
     const bool uct = cfg->evaluator == CK_EVAL_ROLLOUT || cfg->evaluator == CK_EVAL_ROLLOUT_HASH;
     if (cfg->evaluator < CK_EVAL_NET || cfg->evaluator > CK_EVAL_ROLLOUT_HASH) { fail(CK_ERR_ARG, "ck_engine_create: unknown evaluator"); return nullptr; }
     if (cfg->arena && (uct || cfg->evaluator_p2 == CK_EVAL_ROLLOUT || cfg->evaluator_p2 == CK_EVAL_ROLLOUT_HASH)) {

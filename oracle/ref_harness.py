@@ -101,7 +101,13 @@ def reference_modules(with_pipeline=False, compiled=False):
         raise RuntimeError("reference tree not mounted at %s" % REFERENCE_DIR)
     saved = {n: sys.modules.pop(n) for n in _REF_MODULE_NAMES if n in sys.modules}
     saved_path = list(sys.path)
-    sys.path.insert(0, ref_dir)
+    finder = None
+    if compiled:
+        from . import build_ref
+        finder = build_ref.Finder()
+        sys.meta_path.insert(0, finder)
+    else:
+        sys.path.insert(0, ref_dir)
     try:
         ns = types.SimpleNamespace()
         ns.Checkers = importlib.import_module("Checkers")
@@ -113,6 +119,8 @@ def reference_modules(with_pipeline=False, compiled=False):
         yield ns
     finally:
         sys.path[:] = saved_path
+        if finder is not None:
+            sys.meta_path.remove(finder)
         for n in _REF_MODULE_NAMES:
             sys.modules.pop(n, None)
         sys.modules.update(saved)
