@@ -42,7 +42,7 @@ BUDGET = 400
 ROUNDS_PER_STEP = 400
 PREROLL_BUDGET = 8            # sims/move of the opening plies a slot's first game plays before full-budget play (warm start)
 PREROLL_PLIES = 140           # slot i does that for hash(i) mod 140 plies: stages spread over a typical game length
-PREROLL_ROUNDS = 1200         # untimed rounds that take every slot past its warm-start plies
+PREROLL_ROUNDS = 2400         # untimed rounds: every slot past its warm-start plies and a few full-budget moves into its game
 REF_PLIES = 2                 # plies per game of a reference-arm sample (the reference's TERMINATE_CNT knob)
 TOWER_FLOP_PER_POS = 2 * (9 * 14 * 128 * 64 + 7 * 9 * 128 * 128 * 64 + 128 * 8 * 64)   # 134,316,032: the eight 3x3 convs + the policy conv1x1 the tower kernel evaluates
 NET_FLOP_PER_POS = 134865024                                               # SURVEY 8(d), whole network

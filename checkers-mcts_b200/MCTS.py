@@ -165,7 +165,13 @@ class MCTS(object):
             # CONSTRAINT='time' (MCTS.py:193-195): BUDGET seconds of wall clock, checked between batches of
             # simulations (the reference checks before every single one)
             cls.rollout_count = 0
+            cap = eng.pool_cap()
             while (datetime.now() - start).total_seconds() < cls.budget:
+                # the device tree lives in a fixed node pool: a search that could outgrow it stops early with the
+                # simulations it has (the reference's Python tree has no such bound) instead of failing the move
+                if eng.tree_node_count() + cls.time_check_sims * _L.MAX_CHILDREN > cap:
+                    print('Node pool exhausted after {} rollouts: search stopped before its time budget'.format(cls.rollout_count))
+                    break
                 eng.tree_search(cls.time_check_sims)
                 cls.rollout_count += cls.time_check_sims
         root_node._children = None

@@ -166,3 +166,13 @@ def broadcast_int(value, rank, world, device=None, src=0):
     t = torch.tensor([int(value) if rank == src else 0], dtype=torch.int64, device=dev)
     dist.broadcast(t, src=src)
     return int(t.item())
+
+
+def broadcast_strings(values, rank, world, src=0):
+    """a short list of strings (file names; None allowed) from ``src`` to every rank"""
+    import torch.distributed as dist
+    if world == 1:
+        return values
+    box = [list(values) if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]

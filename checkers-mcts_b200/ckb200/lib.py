@@ -114,6 +114,8 @@ def _load():
     L.ck_tree_advance.argtypes = [vp, i32]
     L.ck_tree_node_count.argtypes = [vp]
     L.ck_tree_node_count.restype = i64
+    L.ck_engine_pool_cap.argtypes = [vp]
+    L.ck_engine_pool_cap.restype = i64
     L.ck_tree_epoch.argtypes = [vp]
     L.ck_tree_epoch.restype = i64
     return L
@@ -419,6 +421,9 @@ class Engine(object):
 
     def tree_node_count(self):
         return int(_lib.ck_tree_node_count(self._h))
+
+    def pool_cap(self):
+        return int(_lib.ck_engine_pool_cap(self._h))
 
     def tree_epoch(self):
         return int(_lib.ck_tree_epoch(self._h))

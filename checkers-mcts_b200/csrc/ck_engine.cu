@@ -57,6 +57,8 @@ struct Counters {
     unsigned long long games_finished, moves, nodes, compactions;
     int32_t next_game, error, halted, active;
     int32_t batch_count[2];
+    int32_t deferred;        // leaves that asked for a batch row beyond leaf_cap this round (they ask again next round)
+    int32_t leaf_cap;        // rows the evaluator batch of this round may hold (round_begin_kernel)
 };
 
 struct EngineDev {
@@ -80,6 +82,7 @@ struct EngineDev {
     int32_t cache_entries;       // per slot, a power of two
     int32_t max_chain;           // simulations a slot may complete inside one round without a network evaluation (terminal + cached)
     int32_t cache_game_tag;      // 1: the evaluator depends on the game (salted stubs), so entries are tagged with it
+    int32_t wave;                // positions one full wave of the tower evaluates (tiles x positions per tile x SMs); 0: no batch shaping
 };
 
 // ---- small device helpers --------------------------------------------------------------
@@ -276,11 +279,31 @@ __device__ int select_leaf(const WarpCtx &c, int *out_depth) {
     }
 }
 
-// stage the network input of a leaf (Checkers.predict, Checkers.py:431-432)
+// stage the network input of a leaf (Checkers.predict, Checkers.py:431-432).  The batch of a round is shaped to whole
+// waves of the tower kernel (round_begin_kernel): a leaf that asks for a row beyond the round's cap is not staged and
+// the slot repeats the same descent in the next round -- deterministic (the tree did not change and the exploration
+// noise is keyed by search and simulation number), so results do not depend on which slots had to wait.
 __device__ void stage_leaf(const WarpCtx &c, int leaf, int depth) {
     const EngineDev &E = c.E;
     Slot &S = c.S;
     __syncwarp();
+    if (c.lane == 0) {
+        const int net = net_of(E, S.game, S.cur);
+        if (E.wave > 0) {
+            const int row = atomicAdd(&E.ctr->batch_count[net], 1);
+            if (row >= *(volatile int32_t *)&E.ctr->leaf_cap) {
+                atomicSub(&E.ctr->batch_count[net], 1);
+                atomicAdd(&E.ctr->deferred, 1);
+                leaf = -1;
+            } else {
+                S.pend_row = row;
+            }
+        } else {
+            S.pend_row = atomicAdd(&E.ctr->batch_count[net], 1);
+        }
+    }
+    leaf = __shfl_sync(CK_FULL, leaf, 0);
+    if (leaf < 0) { __syncwarp(); return; }
     if (c.lane == 0) {
         const int net = net_of(E, S.game, S.cur);
         const ck_pos p = to_pos(c.pos_of(S.cur)[leaf]);
@@ -290,9 +313,8 @@ __device__ void stage_leaf(const WarpCtx &c, int leaf, int depth) {
         outcome_of(p, cnt > 0, &p5);
         L.p1 = p.p1; L.p2 = p.p2; L.k = p.k;
         L.info = (p.meta & 1u) | ((uint32_t)p5 << 8) | (((uint32_t)global_game(E, S.game) & 0xFFFFu) << 16);
-        const int row = atomicAdd(&E.ctr->batch_count[net], 1);
-        E.leaves[net][row] = L;
-        S.pend_leaf = leaf; S.pend_row = row; S.pend_depth = depth; S.pend_net = net;
+        E.leaves[net][S.pend_row] = L;
+        S.pend_leaf = leaf; S.pend_depth = depth; S.pend_net = net;
     }
     __syncwarp();
 }
@@ -925,6 +947,24 @@ __global__ void __launch_bounds__(32) manual_compact_kernel(const EngineDev E) {
     }
 }
 
+// Start of a round: shape the coming evaluator batch and zero the round's counters (one tiny launch instead of a
+// memset).  The tower evaluates 4 positions per CTA iteration on every SM, so a batch of k full waves plus a few
+// positions costs k + 1 iterations; at cfg2 with the evaluation cache ~3700 leaves ask for a row per round
+// (6.24 waves -> 7 iterations, the tensor pipe idle 9 % of the launch).  The cap is the request count of the previous
+// round rounded down to whole waves; the leaves beyond it wait one round.  Measured: see DESIGN.md.
+__global__ void round_begin_kernel(const EngineDev E) {
+    Counters *c = E.ctr;
+    if (threadIdx.x == 0) {
+        int cap = 0x7FFFFFFF;
+        if (E.wave > 0) {
+            const int asked = c->batch_count[0] + c->deferred;       // previous round
+            if (asked >= E.wave) cap = asked / E.wave * E.wave;
+        }
+        c->leaf_cap = cap;
+        c->active = 0; c->batch_count[0] = 0; c->batch_count[1] = 0; c->deferred = 0;
+    }
+}
+
 // simulation / evaluation totals live per slot (no hot-path atomics); summed on demand
 __global__ void sum_slots_kernel(const EngineDev E, unsigned long long *out /* sims, evals, cache hits */) {
     unsigned long long s = 0, e = 0, h = 0;
@@ -1166,6 +1206,14 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     }
     d.one_minus_eps = (float)(1.0 - cfg->epsilon);       // (1 - eps) * float32 array stays float32 (numpy >= 2)
     if (cfg->keep_records) d.max_rec = (cfg->terminate_cnt > 0 ? cfg->terminate_cnt : d.max_plies) + 1;
+    // batch shaping only where the tower runs whole waves: self-play with the network, two tiles per CTA
+    {
+        // CK_BATCH_WAVES=0 switches it off; CK_BATCH_WAVES=n (> 1) forces a wave of n rows for every evaluator (tests)
+        static const int shape_env = getenv("CK_BATCH_WAVES") ? atoi(getenv("CK_BATCH_WAVES")) : -1;
+        const int wave = 4 * num_sms(cfg->device);
+        if (shape_env > 1) d.wave = cfg->arena ? 0 : shape_env;
+        else d.wave = (shape_env != 0 && cfg->evaluator == CK_EVAL_NET && !cfg->arena && cfg->n_slots >= 2 * wave) ? wave : 0;
+    }
     CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK_E(cudaEventCreate(&e->ev0)); CK_E(cudaEventCreate(&e->ev1));
     if (cfg->arena) {
@@ -1361,9 +1409,9 @@ static int engine_eval(ck_engine *e, int *launches) {
 // One lock-step round = tree kernel + evaluation of the staged leaves.
 static int engine_round(ck_engine *e, int *launches) {
     EngineDev &d = e->dev;
-    CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));   // active + batch_count[2]
+    round_begin_kernel<<<1, 32, 0, e->stream>>>(d);      // batch cap of the round, counters to zero
     launch_tree_step(e);
-    if (launches) *launches += 1;
+    if (launches) *launches += 2;
     CK_CUDA(cudaGetLastError());
     return engine_eval(e, launches);
 }
@@ -1413,9 +1461,9 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         const int64_t chunk = n_steps > 0 ? std::min<int64_t>(check, n_steps - steps) : check;
         for (int64_t i = 0; i < chunk; ++i) {
             if (e->profile) {
-                CK_CUDA(cudaMemsetAsync(&d.ctr->active, 0, sizeof(int32_t) * 3, e->stream));
+                round_begin_kernel<<<1, 32, 0, e->stream>>>(d);
                 launch_tree_step(e);
-                ++launches;
+                launches += 2;
                 CK_CUDA(cudaEventRecord(e->prof_ev[3 * i], e->stream));
                 if (e->net[0]) e->net[0]->ev_after_tower = e->prof_ev[3 * i + 1];
                 rc = engine_eval(e, &launches);
@@ -1769,6 +1817,8 @@ int ck_tree_reroot(ck_engine *e, int32_t node) {
 }
 
 int64_t ck_tree_epoch(ck_engine *e) { return e ? e->tree_epoch : -1; }
+
+int64_t ck_engine_pool_cap(ck_engine *e) { return e ? e->dev.cap : -1; }
 
 int ck_tree_advance(ck_engine *e, int32_t child_index) {
     int32_t idx[CK_MAX_CHILDREN], b = 0;

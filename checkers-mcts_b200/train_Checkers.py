@@ -75,12 +75,23 @@ def run_iteration(TRAINING_ITERATION, NN_FN=None, NEW_NN_FN=None, SELFPLAY=True,
     sp = dict(default_selfplay_kwargs(TRAINING_ITERATION, NN_FN), **(selfplay_kwargs or {}))
     mk = dict(default_mcts_kwargs(TRAINING_ITERATION), **(mcts_kwargs or {}))
     data_fns = None
+    # under torchrun every rank plays its share of the games; files, training and parameter records are rank 0's
+    # business (the other ranks wait at the barriers and take the new network's file name from rank 0)
+    from ckb200 import dist as _D
+    rank, world, _local = _D.rank_world()
     if SELFPLAY:
         data_fns = generate_Checkers_data(sp, mk).generate_data()
-        record_params('selfplay', **{**sp, **mk})
+        if rank == 0:
+            record_params('selfplay', **{**sp, **mk})
         out['data_fns'] = data_fns
+    _barrier(world)
     tk = dict(default_training_kwargs(TRAINING_ITERATION), **(training_kwargs or {}))
-    if TRAINING:
+    if TRAINING and rank != 0:
+        TRAINING = False                                  # rank 0 trains; the result is broadcast below
+        _names = _D.broadcast_strings([None, None], rank, world)
+        NN_FN, NEW_NN_FN = _names
+        out.update(OLD_NN_FN=NN_FN, NEW_NN_FN=NEW_NN_FN)
+    elif TRAINING:
         if data_fns is not None and not isinstance(data_fns, str) and len(data_fns) > 1:
             merge_data([os.path.basename(fn) for fn in data_fns], TRAINING_ITERATION)   # one file per iteration
             for fn in data_fns:
@@ -96,13 +107,24 @@ def run_iteration(TRAINING_ITERATION, NN_FN=None, NEW_NN_FN=None, SELFPLAY=True,
         tk['OLD_NN_FN'], tk['NEW_NN_FN'] = NN_FN, NEW_NN_FN
         record_params('training', **tk)
         out.update(history=history, OLD_NN_FN=NN_FN, NEW_NN_FN=NEW_NN_FN)
+        if world > 1:
+            _D.broadcast_strings([NN_FN, NEW_NN_FN], rank, world)
+    _barrier(world)
     if EVALUATION:
         tyk = dict(default_tourney_kwargs(TRAINING_ITERATION, NN_FN, NEW_NN_FN), **(tourney_kwargs or {}))
         tmk = dict(default_tourney_mcts_kwargs(NEW_NN_FN), **(tourney_mcts_kwargs or {}))
         print('Beginning tournament between {} and {}!'.format(NEW_NN_FN, NN_FN))
         out['tourney_fn'] = tournament_Checkers(tyk, tmk).start_tournament()
-        record_params('evaluation', **{**tyk, **tmk})
+        if rank == 0:
+            record_params('evaluation', **{**tyk, **tmk})
+    _barrier(world)
     return out
+
+
+def _barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
 
 
 def run_final_evaluation(fe_model_nums, tourney_kwargs=None, tourney_mcts_kwargs=None, num_cpus=4):

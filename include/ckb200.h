@@ -278,6 +278,9 @@ int64_t ck_tree_epoch(ck_engine *);
 /* re-root on the child with this index (MCTS.new_root_node for a one-ply advance) */
 int ck_tree_advance(ck_engine *, int32_t child_index);
 int64_t ck_tree_node_count(ck_engine *);
+/* nodes one tree buffer of this engine can hold (pool_cap after defaults); a search that would exceed it fails with
+ * CK_ERR_POOL_OVERFLOW, so open-ended callers (CONSTRAINT='time') compare it with ck_tree_node_count */
+int64_t ck_engine_pool_cap(ck_engine *);
 
 #ifdef __cplusplus
 }

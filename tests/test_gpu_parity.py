@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, codec, record_planes
+from helpers import GOLDEN, PKG, ROOT, codec, record_planes
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -355,6 +355,44 @@ def test_eval_cache_with_network_and_weight_change(lib):
     assert a[0]["cache_hits"] == 0 and b[0]["cache_hits"] > 0 and b[2]["cache_hits"] > 0
     assert a[0]["nn_evals"] == b[0]["nn_evals"] and a[0]["sims"] == b[0]["sims"]
     net.close()
+
+
+def test_batch_shaping_is_transparent():
+    """the evaluator batch of a round is capped at whole tower waves and the leaves beyond the cap wait a round
+    (round_begin_kernel / stage_leaf).  Forced here to a wave of 5 rows with the salted stub evaluator and 24 slots, so
+    that a large share of the leaves is deferred every round: all records must still equal the oracle's bit for bit."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, json; sys.path[:0] = %r\n"
+        "import numpy as np\n"
+        "from ckb200 import lib\n"
+        "eng = lib.Engine(lib.make_cfg(n_slots=24, budget=48, training=True, terminate_cnt=70, evaluator='hash_salted'))\n"
+        "st = eng.selfplay(40)\n"
+        "r = eng.records(); r = r[np.lexsort((r['ply'], r['game']))]\n"
+        "np.save(sys.argv[1], r); print(json.dumps(dict(steps=st['steps'], sims=st['sims'])))\n") % ([ROOT, PKG],)
+    import tempfile
+    outs = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for waves in ("0", "5"):
+            fn = os.path.join(tmp, "r%s.npy" % waves)
+            r = subprocess.run([sys.executable, "-c", code, fn], env=dict(os.environ, CK_BATCH_WAVES=waves), capture_output=True,
+                               text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            outs[waves] = (np.load(fn), json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = outs["0"], outs["5"]
+    assert a[0].tobytes() == b[0].tobytes() and a[1]["sims"] == b[1]["sims"]
+    assert b[1]["steps"] > 1.5 * a[1]["steps"]              # deferral really happened: the capped run needs many more rounds
+    ref = _oracle_games(40, 48, 70)
+    k = 0
+    for g in range(40):
+        for rr in ref[g][0]:
+            e = a[0][k]
+            n = int(e["n_children"])
+            assert tuple(int(v) for v in e["pos"]) == rr["pos"] and [int(v) for v in e["visits"][:n]] == rr["visits"]
+            assert np.float32(e["root_w"]).tobytes() == np.float32(rr["root_w"]).tobytes()
+            k += 1
+    assert k == len(a[0])
 
 
 def test_packed_records_equal_full_records(lib):
