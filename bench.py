@@ -430,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f32 (split-fp16 tensor-core passes, fp32 accumulate)" if args.net_impl == "tc" else "f32",
             "data": "synthetic", "config": workload_config(world)}
     line["config"]["net_impl"] = args.net_impl
-    line["config"]["eval_cache"] = "off" if args.no_eval_cache else "on (per-slot, 4096 entries)"
+    line["config"]["eval_cache"] = "off" if args.no_eval_cache else "on (per-slot, 16384 entries)"
     line["config"]["steady_state"] = ("warm start: the first game of slot i plays its first hash(i) mod %d plies at %d sims/move and everything "
                                       "after that at %d, so slots reach full-budget play at scattered game stages; untimed pre-roll of %d rounds "
                                       "(%d moves, %d games ended), then %d warm-up steps" %

@@ -83,6 +83,7 @@ struct EngineDev {
     int32_t max_chain;           // simulations a slot may complete inside one round without a network evaluation (terminal + cached)
     int32_t cache_game_tag;      // 1: the evaluator depends on the game (salted stubs), so entries are tagged with it
     int32_t wave;                // positions one full wave of the tower evaluates (tiles x positions per tile x SMs); 0: no batch shaping
+    int32_t wave_slack10;        // the batch is cut back to whole waves while the excess is below wave_slack10 / 10 of a wave
 };
 
 // ---- small device helpers --------------------------------------------------------------
@@ -169,13 +170,13 @@ __device__ void backup(const WarpCtx &c, int depth, bool is_outcome, int outcome
 // Exp(1) from one random word.  A 24-bit uniform and a single-precision logarithm are ample for exploration
 // noise (the sum that enters PUCT is formed in float64 as in the reference); the float64 log was a third of
 // the instructions of a descent.
-__device__ __forceinline__ double exp1_from(uint32_t w) {
-    return (double)(-logf((float)((w >> 8) + 1u) * (1.0f / 16777216.0f)));
+__device__ __forceinline__ float exp1_from(uint32_t w) {
+    return -__logf((float)((w >> 8) + 1u) * (1.0f / 16777216.0f));
 }
 
 __device__ double gamma_sample(const Philox &rng, uint32_t c0, uint32_t c1, uint32_t c2, double alpha) {
     uint32_t r[4];
-    if (alpha == 1.0) { rng(c0, c1, c2, 0x44495231u, r); return exp1_from(r[0]); }
+    if (alpha == 1.0) { rng(c0, c1, c2, 0x44495231u, r); return (double)exp1_from(r[0]); }
     const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
     const double d = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
     double out = d;
@@ -228,8 +229,10 @@ __device__ int select_leaf(const WarpCtx &c, int *out_depth) {
         if (c.lane + 32 < b) c1 = stat[fc + 32 + c.lane];
         double n0 = 0.0, n1 = 0.0;
         if (E.cfg.epsilon != 0.0) {                      // fresh Dirichlet(alpha) at every node, every visit (:107-108)
+            // the noise is exploration only (statistical parity, SURVEY 8b RNG row): gamma variates and their
+            // normalisation in single precision; the sum that enters PUCT is formed in float64 as in the reference
             const uint32_t cc0 = (uint32_t)c.S.search_id, cc1 = (uint32_t)c.S.sims_done;
-            double g0, g1 = 0.0;
+            float g0, g1 = 0.f;
             if (E.cfg.alpha == 1.0) {
                 // Gamma(1) = Exp(1): one Philox block (four words) serves a child slot for four consecutive
                 // levels of the descent -- word depth & 3 of the block keyed by (search, simulation, depth / 4, child)
@@ -237,33 +240,33 @@ __device__ int select_leaf(const WarpCtx &c, int *out_depth) {
                     rng(cc0, cc1, (uint32_t)((depth >> 2) << 8 | c.lane), 0x44495231u, noise_a);
                 }
                 const uint32_t w = (depth & 2) ? ((depth & 1) ? noise_a[3] : noise_a[2]) : ((depth & 1) ? noise_a[1] : noise_a[0]);
-                g0 = c.lane < b ? exp1_from(w) : 0.0;
+                g0 = c.lane < b ? exp1_from(w) : 0.f;
                 // more than 32 children is rare: those slots draw their own block per level
-                if (c.lane + 32 < b) g1 = gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), 1.0);
+                if (c.lane + 32 < b) g1 = (float)gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), 1.0);
             } else {
-                g0 = c.lane < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | c.lane), E.cfg.alpha) : 0.0;
-                g1 = c.lane + 32 < b ? gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), E.cfg.alpha) : 0.0;
+                g0 = c.lane < b ? (float)gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | c.lane), E.cfg.alpha) : 0.f;
+                g1 = c.lane + 32 < b ? (float)gamma_sample(rng, cc0, cc1, (uint32_t)(depth << 8 | (c.lane + 32)), E.cfg.alpha) : 0.f;
             }
-            double tot = g0 + g1;
+            float tot = g0 + g1;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) tot += shfl_xor_d(tot, o);
-            n0 = g0 / tot; n1 = g1 / tot;
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(CK_FULL, tot, o);
+            const float inv = __fdividef(1.0f, tot);
+            n0 = (double)(g0 * inv); n1 = (double)(g1 * inv);
         }
-        double best_u = 0.0;
-        int best_i = kNoIdx;
-        if (c.lane < b) { best_u = puct(E, c0, n0, sqrt_n); best_i = c.lane; }
-        if (c.lane + 32 < b) {
-            const double u1 = puct(E, c1, n1, sqrt_n);
-            if (u1 > best_u) { best_u = u1; best_i = c.lane + 32; }    // np.argmax: first maximum wins
-        }
+        // arg-max with np.argmax's tie rule (first maximum, MCTS.py:116): butterfly maximum of the scores -- only the
+        // rounds the child count needs, lanes beyond it hold -inf --, then the first lane that holds it
+        const double kNegInf = __longlong_as_double(0xFFF0000000000000ll);
+        const double u0 = c.lane < b ? puct(E, c0, n0, sqrt_n) : kNegInf;
+        const double u1 = c.lane + 32 < b ? puct(E, c1, n1, sqrt_n) : kNegInf;
+        double m = fmax(u0, u1);
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const double ou = shfl_xor_d(best_u, o);
-            const int oi = __shfl_xor_sync(CK_FULL, best_i, o);
-            const bool take = (oi != kNoIdx) && (best_i == kNoIdx || ou > best_u || (ou == best_u && oi < best_i));
-            if (take) { best_u = ou; best_i = oi; }
-        }
-        best_i = __shfl_sync(CK_FULL, best_i, 0);       // lanes agree by construction unless scores are NaN (a network out of range): stay converged
+        for (int o = 1; o < 32; o <<= 1)
+            if (o < b) m = fmax(m, shfl_xor_d(m, o));                               // b is warp-uniform
+        const uint32_t lt = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+        const uint32_t first0 = __ballot_sync(CK_FULL, u0 == m) & lt;
+        const uint32_t first1 = b > 32 ? __ballot_sync(CK_FULL, u1 == m) & ((1u << (b - 32)) - 1u) : 0u;
+        // scores are never NaN unless the network left its range (reported as CK_ERR_NET_RANGE): child 0 then
+        int best_i = first0 ? __ffs((int)first0) - 1 : first1 ? 32 + __ffs((int)first1) - 1 : 0;
         const uint4 pick = best_i < 32 ? shfl4(c0, best_i) : shfl4(c1, best_i - 32);
         node = fc + best_i;
         ++depth;
@@ -957,8 +960,12 @@ __global__ void round_begin_kernel(const EngineDev E) {
     if (threadIdx.x == 0) {
         int cap = 0x7FFFFFFF;
         if (E.wave > 0) {
+            // a leaf that waits costs its slot a whole evaluate-then-chain cycle (~2.4 simulations at cfg2), a wave iteration
+            // saved is worth ~590 of them: cutting the batch back pays while the excess is below ~0.5 wave (measured
+            // break-even, profiles/r2e_steady_sweep.jsonl); applied below 0.3 wave
             const int asked = c->batch_count[0] + c->deferred;       // previous round
-            if (asked >= E.wave) cap = asked / E.wave * E.wave;
+            const int full = asked / E.wave * E.wave;
+            if (full >= E.wave && (asked - full) * 10 < E.wave_slack10 * E.wave) cap = full;
         }
         c->leaf_cap = cap;
         c->active = 0; c->batch_count[0] = 0; c->batch_count[1] = 0; c->deferred = 0;
@@ -1195,10 +1202,11 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     d.max_term = cfg->max_terminal_sims_per_step > 0 ? cfg->max_terminal_sims_per_step : 4;
     d.max_chain = cfg->max_chain_per_step > 0 ? cfg->max_chain_per_step : 8;
     if (d.max_chain < d.max_term) d.max_chain = d.max_term;
-    // evaluation cache: per slot a power of two of 128-byte entries (default 4096 = 512 KB per slot); the playout
-    // modes have no network, the uniform stubs nothing worth caching (but they exercise the path in the tests)
+    // evaluation cache: per slot a power of two of 128-byte entries (default 16384 = 2 MB per slot, 8.6 GB at cfg2: hit
+    // rate 41.8 % / 44.1 % at 4096 / 16384 entries in the warm-started bench, +4 % simulations/s); the playout modes
+    // have no network, the uniform stubs nothing worth caching (but they exercise the path in the tests)
     if (!uct && cfg->eval_cache_entries >= 0) {
-        int want = cfg->eval_cache_entries > 0 ? cfg->eval_cache_entries : 4096;
+        int want = cfg->eval_cache_entries > 0 ? cfg->eval_cache_entries : 16384;
         int ent = 16;
         while (ent < want && ent < (1 << 20)) ent *= 2;
         d.cache_entries = ent;
@@ -1211,6 +1219,7 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         // CK_BATCH_WAVES=0 switches it off; CK_BATCH_WAVES=n (> 1) forces a wave of n rows for every evaluator (tests)
         static const int shape_env = getenv("CK_BATCH_WAVES") ? atoi(getenv("CK_BATCH_WAVES")) : -1;
         const int wave = 4 * num_sms(cfg->device);
+        d.wave_slack10 = shape_env > 1 ? 10 : 3;                 // forced mode always cuts back (every round defers leaves)
         if (shape_env > 1) d.wave = cfg->arena ? 0 : shape_env;
         else d.wave = (shape_env != 0 && cfg->evaluator == CK_EVAL_NET && !cfg->arena && cfg->n_slots >= 2 * wave) ? wave : 0;
     }

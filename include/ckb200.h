@@ -157,7 +157,7 @@ typedef struct {
     int32_t game_id_stride;   /* 0 is treated as 1 */
     int32_t max_terminal_sims_per_step; /* simulations ending in a terminal child that a slot may finish inside one round; 0: default 4 */
     int32_t compact_always;   /* 1: compact the kept subtree at every re-root (default: only when the pool runs low) */
-    int32_t eval_cache_entries; /* evaluation cache entries per slot (128 B each, rounded up to a power of two); 0: default 4096;
+    int32_t eval_cache_entries; /* evaluation cache entries per slot (128 B each, rounded up to a power of two); 0: default 16384;
                                  * < 0: no cache.  A leaf whose network input (position, side to move, plane 5) was evaluated
                                  * before in the same slot is expanded from the cached priors / value: same numbers, no network call */
     int32_t max_chain_per_step; /* simulations a slot may complete inside one round without a network evaluation

