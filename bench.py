@@ -253,8 +253,8 @@ def pipeline_e2e(dev, rank, world, n_games, num_cpus):
     import training_pipeline as TP
     from ckb200 import net as N
     work = tempfile.mkdtemp(prefix="ckb200_pipe_%d_" % rank)
-    free = shutil.disk_usage(work).free
-    need = n_games * 150 * 12000 * 1.2                      # ~150 records per game x 11.8 KB in the reference's format
+    free = shutil.disk_usage(work).free / max(world, 1)     # every rank writes its own files at the same time
+    need = n_games * 150 * 12000 * 1.5                      # ~150 records per game x 11.8 KB in the reference's format, with headroom
     if free < need:
         n_games = max(num_cpus, int(n_games * free / need / num_cpus) * num_cpus)
     os.makedirs(os.path.join(work, "data", "training_data"))

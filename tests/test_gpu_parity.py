@@ -357,6 +357,53 @@ def test_eval_cache_with_network_and_weight_change(lib):
     net.close()
 
 
+def test_baseline_size_records_vs_oracle(lib):
+    """BASELINE configs[1] size -- 4096 concurrent games, 400 sims/move -- against the oracle: every game's evaluator is
+    salted with its id, 64 sampled games (first, last, and spread over the slots) must equal the oracle's records bit
+    for bit, i.e. nothing leaks between the 4096 trees, their caches and their batch rows at full size."""
+    n_games, budget, term = 4096, 400, 5
+    eng = lib.Engine(lib.make_cfg(n_slots=n_games, budget=budget, training=True, terminate_cnt=term, evaluator="hash_salted"))
+    st = eng.selfplay(n_games)
+    recs, games = _engine_records(lib, eng)
+    eng.close()
+    assert st["games_finished"] == n_games and st["sims"] == n_games * term * budget
+    sample = sorted(set([0, 1, 2, 4095, 4094] + list(range(7, 4096, 69))))[:64]
+    for g in sample:
+        gm = O.Game(O.make_cfg(budget=budget, training=True, terminate_cnt=term), "hash_salted", None, salt=g)
+        gm.play()
+        rr = gm.records()
+        assert int(games[g]["outcome"]) == gm.outcome and int(games[g]["move_count"]) == gm.move_count
+        assert int(games[g]["sims"]) == gm.total_sims and int(games[g]["nn_evals"]) == gm.nn_evals
+        assert len(recs[g]) == len(rr) and all(_same_record(a, b) for a, b in zip(recs[g], rr)), g
+        gm.close()
+
+
+def test_reference_tau_quirk(lib):
+    """MCTS(**kwargs) runs once per worker process in the reference (training_pipeline.py:347), so the temperature is
+    never reset: only a worker's first game samples with tau > 0, every later game is pure arg-max play.  With
+    reference_tau_quirk the second game of a slot therefore equals the oracle's game at tau = 0; without it the
+    temperature starts again at TEMPERATURE_TAU."""
+    kw = dict(budget=60, training=True, terminate_cnt=30, evaluator="hash", tau=1.0, tau_decay=0.5, tau_decay_delay=2, seed=9)
+    gm = O.Game(O.make_cfg(budget=60, training=True, terminate_cnt=30, tau=0.0), "hash", None)
+    gm.play()
+    ref = gm.records()
+    gm.close()
+
+    def second_game(quirk):
+        eng = lib.Engine(lib.make_cfg(n_slots=1, reference_tau_quirk=quirk, **kw))
+        eng.selfplay(2)
+        recs, _games = _engine_records(lib, eng)
+        eng.close()
+        return recs[0], recs[1]
+
+    first, second = second_game(True)
+    assert len(second) == len(ref) and all(_same_record(a, b) for a, b in zip(second, ref))
+    first2, second2 = second_game(False)
+    assert all(_same_record(a, b) for a, b in zip(first, first2)) and len(first) == len(first2)     # the first game is the same either way
+    chosen = lambda rr: [r["chosen"] for r in rr]
+    assert chosen(second2)[:8] != chosen(ref)[:8] or chosen(second2) != chosen(ref)      # temperature back on: sampled moves
+
+
 def test_batch_shaping_is_transparent():
     """the evaluator batch of a round is capped at whole tower waves and the leaves beyond the cap wait a round
     (round_begin_kernel / stage_leaf).  Forced here to a wave of 5 rows with the salted stub evaluator and 24 slots, so
