@@ -399,12 +399,13 @@ def run_ours(args, rank, world, local_rank):
     sims, evals, games, moves, e2e_sims, launches, hits, e2e_games = w.tolist()
 
     # ---- outside the timed region ------------------------------------------------------------------
-    gather_ms, pooled_n, gather_bytes, shard_check = None, None, None, None
+    gather_ms, pooled_n, gather_bytes, shard_check, decode_ms = None, None, None, None, None
     if world > 1:
         # the iteration-end NCCL gather of the finished games' records, packed on the device (ckb200.dist)
+        D.warm_up_p2p(rank, world, "cuda:%d" % dev)               # NCCL opens point-to-point channels at first use
         pooled, info = D.gather_engine_records(eng, rank, world, "cuda:%d" % dev, want_info=True)
         if rank == 0:
-            gather_ms, pooled_n, gather_bytes = info["ms"], int(len(pooled)), info["bytes"]
+            gather_ms, pooled_n, gather_bytes, decode_ms = info["gather_ms"], int(len(pooled)), info["bytes"], info["decode_ms"]
         del pooled
     eng.close()
     if world > 1:
@@ -451,7 +452,8 @@ def run_ours(args, rank, world, local_rank):
     line["gpu_launches"] = int(launches)
     line["clocks"] = clocks
     if gather_ms is not None:
-        line["records_gather_ms"] = gather_ms
+        line["records_gather_ms"] = gather_ms              # device-side packing + exact-size NCCL send/recv into rank 0's HBM
+        line["records_decode_ms"] = decode_ms              # rank 0: D2H + numpy decode into ck_record structs
         line["records_pooled"] = pooled_n
         line["records_gather_bytes"] = gather_bytes
     if shard_check is not None:

@@ -91,12 +91,14 @@ def gather_packed(hdr, words, rank, world, device=None, dst=0):
     return H, W, sizes
 
 
-def gather_engine_records(engine, rank, world, device, dst=0, want_info=False):
+def gather_engine_records(engine, rank, world, device, dst=0, want_info=False, unpack=True):
     """The iteration-end gather (the reference's Pool.map return + merge_data, training_pipeline.py:277-284, 323-332):
     every rank packs the records of its finished games ON THE DEVICE into two torch buffers (ck_records_pack_device,
-    ~75 bytes per record instead of 372), ``dst`` receives them with exact-size NCCL point-to-point transfers and
-    unpacks once.  -> (RECORD_DTYPE array of all ranks ordered by rank on ``dst`` / None elsewhere, milliseconds), or with
-    ``want_info`` a dict(ms, bytes) in place of the milliseconds."""
+    ~60-75 bytes per record instead of 372), ``dst`` receives them with exact-size NCCL point-to-point transfers straight
+    into device memory and decodes once on the host.  -> (RECORD_DTYPE array of all ranks ordered by rank on ``dst`` /
+    None elsewhere, milliseconds), or with ``want_info`` a dict in place of the milliseconds: ``gather_ms`` = packing +
+    NCCL transfers (everything up to "all records are in rank 0's HBM"), ``decode_ms`` = D2H copy + numpy decode into
+    RECORD_DTYPE, ``ms`` their sum, ``bytes`` on the wire.  ``unpack=False`` returns (headers, words) instead of decoding."""
     import time
     import torch
     from . import records as R
@@ -114,6 +116,8 @@ def gather_engine_records(engine, rank, world, device, dst=0, want_info=False):
         got = gather_packed(h, w, rank, world, device=dev, dst=dst)
     else:
         got = (h, w, [(h.numel(), w.numel())])
+    torch.cuda.synchronize(dev)
+    t1 = time.time()
     out = None
     nbytes = 0
     if got is not None:
@@ -121,10 +125,19 @@ def gather_engine_records(engine, rank, world, device, dst=0, want_info=False):
         nbytes = H.numel() + 4 * W.numel()
         hdr = H.cpu().numpy().view(RECORD_HDR_DTYPE)
         words = W.cpu().numpy().view(np.uint32)
-        out = R.unpack(hdr, words)
-    torch.cuda.synchronize(dev)
-    ms = 1000.0 * (time.time() - t0)
-    return (out, dict(ms=ms, bytes=nbytes)) if want_info else (out, ms)
+        out = R.unpack(hdr, words) if unpack else (hdr, words)
+    t2 = time.time()
+    info = dict(ms=1000.0 * (t2 - t0), gather_ms=1000.0 * (t1 - t0), decode_ms=1000.0 * (t2 - t1), bytes=nbytes)
+    return (out, info) if want_info else (out, info["ms"])
+
+
+def warm_up_p2p(rank, world, device, dst=0):
+    """NCCL opens its point-to-point channels lazily at the first send/recv between two ranks (hundreds of milliseconds
+    for seven peers); one tiny exchange up front keeps that one-off cost out of a timed gather"""
+    import torch
+    if world > 1:
+        gather_packed(torch.zeros(40, dtype=torch.uint8, device=device), torch.zeros(1, dtype=torch.int32, device=device),
+                      rank, world, device=device, dst=dst)
 
 
 def rank_world():

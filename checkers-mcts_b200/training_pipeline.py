@@ -250,6 +250,8 @@ class generate_Checkers_data(object):
         spec = self.mcts_kwargs.get('PLAYOUT_EVALUATOR', 'rollout') if playouts else load_blob(self.nn_fn)
         base, stride, n_local = _D.shard(total, rank, world)
         recs, games = _np_empty(_L.RECORD_DTYPE), _np_empty(_L.GAME_DTYPE)
+        import time as _time
+        _t_host = _time.time()
         if n_local > 0:
             cfg = _engine_cfg(self.mcts_kwargs, min(n_local, self.max_slots), self.TERMINATE_CNT,
                               spec if isinstance(spec, str) else "net", device=device, seed=seed,
@@ -258,6 +260,7 @@ class generate_Checkers_data(object):
             try:
                 net = _attach(eng, 0, spec, device)
                 self.stats = eng.selfplay(n_local)
+                _t_host = _time.time()                    # everything from here on is host-side work on finished games
                 games = eng.games()
                 if world > 1:                             # packed on the device, exact-size NCCL transfers to rank 0
                     recs, _ms = _D.gather_engine_records(eng, rank, world, "cuda:%d" % device)
@@ -273,8 +276,6 @@ class generate_Checkers_data(object):
             games = _D.gather_records(games, rank, world, device="cuda:%d" % device)
             if rank != 0:
                 return []
-        import time as _time
-        _t_host = _time.time()
         recs = recs[np.argsort(recs["game"], kind="stable")]       # game by game, plies in order
         games = games[np.argsort(games["game"], kind="stable")]
         names = {1: 'player1_wins', 2: 'player2_wins', 3: 'draw'}

@@ -67,6 +67,7 @@ def main():
         torch.cuda.synchronize()
         wall = time.time() - t0
         games = eng.games()
+        D.warm_up_p2p(rank, world, dev)
         pooled, info = D.gather_engine_records(eng, rank, world, dev, want_info=True)
         (gpu_ms, wall_max), (sims, evals, hits, moves, ngames, nrec) = reduce(
             dev, [st["gpu_ms"], wall], [st["sims"], st["nn_evals"], st["cache_hits"], st["moves"], len(games), eng.records_packed_sizes()[0]])
@@ -78,7 +79,7 @@ def main():
                                   "sims_per_sec": sims / (gpu_ms / 1e3), "games_per_sec": ngames / (gpu_ms / 1e3), "gpu_s_max_over_ranks": gpu_ms / 1e3,
                                   "wall_s_max_over_ranks": wall_max, "sims": sims, "moves": moves, "plies_per_game": moves / max(ngames, 1),
                                   "eval_cache_hit_rate": hits / max(evals, 1), "network_evals": evals - hits, "records": int(nrec),
-                                  "records_pooled_on_rank0": int(len(pooled)), "records_gather_ms": info["ms"], "records_gather_bytes": info["bytes"],
+                                  "records_pooled_on_rank0": int(len(pooled)), "records_gather_ms": info["gather_ms"], "records_decode_ms": info["decode_ms"], "records_gather_bytes": info["bytes"],
                                   "outcomes_p1_p2_draw": [int(v) for v in oc]}) + "\n")
             out.flush()
         del pooled
