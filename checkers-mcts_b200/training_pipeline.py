@@ -409,14 +409,27 @@ class final_evaluation(object):
         self.game_outcomes = []
 
     def start_evaluation(self, num_cpus=1):
-        """num_cpus is accepted for compatibility; each pairing is one two-game arena on the GPU"""
+        """Every pairing is one two-game arena (training_pipeline.py:632-658).  The reference fans the pairings of one
+        "new" model out over ``num_cpus`` processes; here up to ``max(num_cpus, 16)`` pairings run CONCURRENTLY on the
+        GPU, each in its own engine on its own stream (the library calls release the GIL), because a two-game arena by
+        itself is pure launch latency.  Under torchrun the pairings run one after the other (their games shard over
+        the ranks and the collectives must stay ordered)."""
         model_fn_list = self.model_fn_list.copy()
-        for _ in range(len(self.model_fn_list) - 1):
+        pairings = []                                     # (group index, new, old) in the reference's order
+        for grp in range(len(self.model_fn_list) - 1):
             new_nn_fn = model_fn_list.pop()
-            game_outcomes = []
-            for old_nn_fn in model_fn_list:
-                game_outcomes.extend(self._wrapper_func(new_nn_fn, old_nn_fn))
-            self.game_outcomes.append(game_outcomes)
+            pairings += [(grp, new_nn_fn, old_nn_fn) for old_nn_fn in model_fn_list]
+        world = _D.rank_world()[1]
+        if world == 1 and len(pairings) > 1:
+            import concurrent.futures as cf
+            with cf.ThreadPoolExecutor(max_workers=min(len(pairings), max(int(num_cpus), 16))) as pool:
+                results = list(pool.map(lambda p: self._wrapper_func(p[1], p[2]), pairings))
+        else:
+            results = [self._wrapper_func(p[1], p[2]) for p in pairings]
+        groups = [[] for _ in range(len(self.model_fn_list) - 1)]
+        for (grp, _new, _old), rows in zip(pairings, results):
+            groups[grp].extend(rows)
+        self.game_outcomes.extend(groups)
         if _D.rank_world()[0] != 0:                       # rank 0 holds the pooled results of a multi-GPU run
             return None
         filename = self._parse_tourney_results()
