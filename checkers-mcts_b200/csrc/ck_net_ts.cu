@@ -49,7 +49,15 @@ constexpr int kTileBytes = 2 * kSplitBytes;
 constexpr int kKSteps0 = 9, kKStepsL = 72;          // k-steps (16 input channels of one tap) per layer
 constexpr int kKSteps8 = 8;                          // "layer 8": the policy head's 1x1 conv 128 -> 8, centre tap only
 constexpr int kLayers = kTowerConvs + 1;            // 8 3x3 convolutions + the fused policy conv1x1
-constexpr int kG = kKSteps0 + 7 * kKStepsL + kKSteps8;   // 521 k-steps = the whole weight stream
+constexpr int kG = kKSteps0 + 7 * kKStepsL + kKSteps8;   // 521 k-steps = the whole weight stream (interleaved order)
+// "Cross terms first" order (the product path).  The tensor pipe rounds its fp32 accumulator toward zero after every MMA,
+// so a chain of 216 MMAs into one accumulator loses ~1e-5 relative in one direction.  Two thirds of
+// those MMAs add the 2^-11-sized cross terms Whi*Alo + Wlo*Ahi: issued FIRST, while the accumulator is still tiny, their
+// roundings cost nothing, and only the 72 Whi*Ahi MMAs round at full magnitude.  Price: a layer's Whi is streamed twice.
+// A weight slot (16 TMEM columns) then holds either (Whi, Wlo) of one k-step [phase A: 2 cross MMAs] or Whi of two
+// consecutive k-steps [phase B: 2 main MMAs], so every slot still feeds exactly two MMAs per tile.
+__host__ __device__ constexpr int cf_slots(int ksteps) { return ksteps + (ksteps + 1) / 2; }
+constexpr int kGcf = cf_slots(kKSteps0) + 7 * cf_slots(kKStepsL) + cf_slots(kKSteps8);   // 14 + 7 * 108 + 12 = 782 slot images
 constexpr int kNS = 16;                             // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
 constexpr int kLoaderWarps = 8;                     // two sets of four (one warp per TMEM lane quadrant)
@@ -60,6 +68,7 @@ constexpr float kActScale = 16.0f;                  // activations are stored as
 #endif
 constexpr unsigned kPollNs = CK_POLL_NS;            // epilogue warps sleep this long between polls of the two accumulator barriers
 constexpr size_t kWtsBytes = (size_t)kG * 8192;     // [k-step][unit 4][co 128][16 B]
+constexpr size_t kWtsBytesCf = (size_t)kGcf * 8192; // [slot image][unit 4][co 128][16 B]
 // All CTAs stream the same 4.3 MB (L2-resident after the first tile pair).  kCopies > 1 replicates the
 // packed weights so that CTA b reads copy b % kCopies; measured no difference on B200 (the L2 serves the
 // lock-step readers from one copy at the same rate), so one copy is kept.
@@ -85,6 +94,7 @@ struct TowerParams {
     float *pflat;                // fp32 [n][512]: policy conv1x1 + ReLU + BN, flattened in (x, y, c) order
     float *vconv;                // fp32 [n][64]: value conv1x1 + ReLU + BN
     const float *plane5;         // 81-entry float32(n/80) table
+    const uint4 *wts_cf;         // the same weights as slot images in cross-terms-first order
     int32_t *range_flag;         // set to 1 when an activation leaves the split-fp16 range (|a| * 2^4 >= 65504)
 };
 
@@ -95,10 +105,11 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     return v;
 }
 
-template <int kEpiWarps>
+template <int kEpiWarps, bool kCrossFirst>
 __global__ void __launch_bounds__((kLoaderWarps + 2 + kEpiWarps) * 32, 1)
 tower_ts_kernel(const TowerParams prm) {
     static_assert(kEpiWarps == 8, "epilogue: two warps per TMEM lane quadrant, 64 accumulator columns each");
+    constexpr int kGs = kCrossFirst ? kGcf : kG;                    // weight slots one tile pair consumes
     constexpr int kMmaWarp0 = kLoaderWarps + kEpiWarps;            // warps kMmaWarp0 (tile X) and kMmaWarp0 + 1 (tile Y)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -108,7 +119,7 @@ tower_ts_kernel(const TowerParams prm) {
     const int n_pairs = (n + ppi - 1) / ppi;
     if ((int)blockIdx.x >= n_pairs) return;
     const uint32_t np = (uint32_t)(n_pairs - 1 - (int)blockIdx.x) / gridDim.x + 1;   // tile pairs of this CTA
-    const uint32_t total = np * (uint32_t)kG;                                        // k-steps this CTA streams
+    const uint32_t total = np * (uint32_t)kGs;                                       // weight slots this CTA streams
 
     const uint32_t bar0 = smem_u32(smem + kBarOff);
     auto bar_full = [&](uint32_t s) { return bar0 + 8u * s; };
@@ -144,13 +155,13 @@ tower_ts_kernel(const TowerParams prm) {
         // scoreboard, so deeper per-warp prefetch does not overlap), and the other set's batch covers
         // its latency. =====
         const int set = warp >> 2, quad = warp & 3;
-        const uint4 *src = prm.wts + (size_t)(blockIdx.x % kCopies) * (kWtsBytes / 16) + (quad * 32 + lane);
+        const uint4 *src = (kCrossFirst ? prm.wts_cf : prm.wts + (size_t)(blockIdx.x % kCopies) * (kWtsBytes / 16)) + (quad * 32 + lane);
         const uint32_t t_w = ((uint32_t)(quad * 32) << 16) + kWCol0;
         uint32_t r[kLoadGroup][16];
         for (uint32_t base = (uint32_t)(set * kLoadGroup); base < total; base += 2 * kLoadGroup) {
 #pragma unroll
             for (int j = 0; j < kLoadGroup; ++j) {
-                const uint32_t g = (base + j) % (uint32_t)kG;            // reads past `total` stay inside the stream
+                const uint32_t g = (base + j) % (uint32_t)kGs;           // reads past `total` stay inside the stream
                 const uint4 *p = src + (size_t)g * 512;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -200,6 +211,51 @@ tower_ts_kernel(const TowerParams prm) {
                 const int nk = layer == 0 ? 1 : 8;
                 const int tap_lo = layer == kLayers - 1 ? 4 : 0, tap_hi = layer == kLayers - 1 ? 5 : 9;   // conv1x1 = centre tap
                 uint32_t acc = 0u;
+                if (kCrossFirst) {
+                    // phase A: the cross terms of every k-step of the layer (slot = Whi | Wlo of one k-step)
+                    for (int tap = tap_lo; tap < tap_hi; ++tap) {
+                        uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
+#pragma unroll 1
+                        for (int kc = 0; kc < nk; ++kc, ++s) {
+                            const uint32_t slot = s & (kNS - 1);
+                            mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                            tc_fence_after();
+                            const uint64_t bhi = kDescHi | (uint64_t)(kDescLo + b);
+                            tc_pair_ts_elect(d, kWCol0 + slot * 16, bhi + (uint64_t)(kSplitBytes >> 4),      // Whi * Alo
+                                             kWCol0 + slot * 16 + 8, bhi, kIdesc, acc, bar_empty(slot));     // Wlo * Ahi
+                            acc = 1u;
+                            b += (uint32_t)(2 * kChunkStride) >> 4;
+                        }
+                    }
+                    // phase B: Whi * Ahi, two consecutive k-steps per slot
+                    if (layer == 0) {
+                        // nine k-steps (one per tap, 16 input channels): pairs of taps, the tenth half-slot holds zeros
+#pragma unroll 1
+                        for (int j = 0; j < 5; ++j, ++s) {
+                            const uint32_t slot = s & (kNS - 1);
+                            mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                            tc_fence_after();
+                            const int t0 = 2 * j, t1 = 2 * j + 1 < 9 ? 2 * j + 1 : 2 * j;
+                            const uint32_t b0 = tile16 + (uint32_t)(kP * (t0 / 3) * 10 + t0 % 3), b1 = tile16 + (uint32_t)(kP * (t1 / 3) * 10 + t1 % 3);
+                            tc_pair_ts_elect(d, kWCol0 + slot * 16, kDescHi | (uint64_t)(kDescLo + b0),
+                                             kWCol0 + slot * 16 + 8, kDescHi | (uint64_t)(kDescLo + b1), kIdesc, 1u, bar_empty(slot));
+                        }
+                    } else {
+                        for (int tap = tap_lo; tap < tap_hi; ++tap) {
+                            uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
+#pragma unroll 1
+                            for (int kc = 0; kc < 8; kc += 2, ++s) {
+                                const uint32_t slot = s & (kNS - 1);
+                                mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                                tc_fence_after();
+                                const uint64_t b0 = kDescHi | (uint64_t)(kDescLo + b);
+                                tc_pair_ts_elect(d, kWCol0 + slot * 16, b0, kWCol0 + slot * 16 + 8, b0 + (uint64_t)((2 * kChunkStride) >> 4),
+                                                 kIdesc, 1u, bar_empty(slot));
+                                b += (uint32_t)(4 * kChunkStride) >> 4;
+                            }
+                        }
+                    }
+                } else
                 for (int tap = tap_lo; tap < tap_hi; ++tap) {
                     uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);     // sq_off(0, tap / 3, tap % 3) / 16
 #pragma unroll 1
@@ -449,13 +505,46 @@ __global__ void wpack_kernel(const float *__restrict__ blob, PackAux aux, const 
     }
 }
 
+// cross-terms-first stream: slot images [unit 0,1: first operand half (columns 0-7), unit 2,3: second half][co].
+// Phase-A image of k-step k: (Whi_k | Wlo_k); phase-B image j: (Whi_2j | Whi_2j+1), zeros beyond the layer's last k-step.
+__global__ void wpack_cf_kernel(const float *__restrict__ blob, PackAux aux, const float *__restrict__ wscale, uint4 *__restrict__ out) {
+    const int64_t total = (int64_t)kGcf * 512;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i & 127), u = (int)((i >> 7) & 3);
+        int g = (int)(i >> 9);
+        int layer = 0, ksteps = kKSteps0;
+        while (g >= cf_slots(ksteps)) { g -= cf_slots(ksteps); ++layer; ksteps = layer < kTowerConvs ? kKStepsL : kKSteps8; }
+        int kstep;
+        bool lo;
+        if (g < ksteps) { kstep = g; lo = (u & 2) != 0; }                       // phase A: hi | lo of one k-step
+        else { kstep = 2 * (g - ksteps) + ((u & 2) ? 1 : 0); lo = false; }      // phase B: hi of two k-steps
+        int tap, ci0;
+        if (layer == 0) { tap = kstep; ci0 = 0; }
+        else if (layer < kTowerConvs) { tap = kstep >> 3; ci0 = (kstep & 7) * 16; }
+        else { tap = 0; ci0 = kstep * 16; }
+        const int cin = aux.cin[layer];
+        const int cout = layer < kTowerConvs ? kC : 8;
+        const float S = wscale[layer];
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = ci0 + (u & 1) * 8 + e;
+            float w = 0.f;
+            if (kstep < ksteps && ci < cin && co < cout) w = blob[aux.koff[layer] + ((int64_t)tap * cin + ci) * cout + co] * S;
+            const __half hi = __float2half_rn(w);
+            h[e] = lo ? __float2half_rn(w - __half2float(hi)) : hi;
+        }
+        out[i] = *reinterpret_cast<const uint4 *>(h);
+    }
+}
+
 }  // namespace ts
 
 int net_ts_prepare(ck_net *net) {
     const NetLayout L = net_layout();
     if (!net->d_wts) {
-        // kCopies x [packed weights], then [wscale 16 f][inv 16 f][plane5 81 f]
-        CK_CUDA(cudaMalloc(&net->d_wts, ts::kCopies * ts::kWtsBytes + 1024));
+        // kCopies x [packed weights], then [wscale 16 f][inv 16 f][plane5 81 f], then the cross-terms-first stream
+        CK_CUDA(cudaMalloc(&net->d_wts, ts::kCopies * ts::kWtsBytes + 1024 + ts::kWtsBytesCf));
     }
     float *aux = (float *)((uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes);
     ts::PackAux h;
@@ -466,23 +555,24 @@ int net_ts_prepare(ck_net *net) {
     CK_CUDA(cudaMemcpy(aux + 32, p5, sizeof(p5), cudaMemcpyHostToDevice));
     ts::wscale_kernel<<<ts::kLayers, 256>>>(net->d_blob, h, aux, aux + 16);
     ts::wpack_kernel<<<1024, 256>>>(net->d_blob, h, aux, (uint4 *)net->d_wts);
+    ts::wpack_cf_kernel<<<1024, 256>>>(net->d_blob, h, aux, (uint4 *)((uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes + 1024));
     CK_CUDA(cudaGetLastError());
     for (int c = 1; c < ts::kCopies; ++c)
         CK_CUDA(cudaMemcpyAsync((uint8_t *)net->d_wts + c * ts::kWtsBytes, net->d_wts, ts::kWtsBytes, cudaMemcpyDeviceToDevice, 0));
     return CK_OK;
 }
 
-template <int kEpiWarps>
+template <int kEpiWarps, bool kCrossFirst>
 static int launch_tower_ts(ck_net *net, const ts::TowerParams &prm, int64_t max_n, cudaStream_t stream) {
     static bool attr_done[64] = {false};          // per device (and per template instantiation)
     static_assert(ts::kSmem <= 232448, "tower tiles do not fit in shared memory");
     if (!attr_done[net->device & 63]) {
-        CK_CUDA(cudaFuncSetAttribute(ts::tower_ts_kernel<kEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmem));
+        CK_CUDA(cudaFuncSetAttribute(ts::tower_ts_kernel<kEpiWarps, kCrossFirst>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::kSmem));
         attr_done[net->device & 63] = true;
     }
     const int64_t pairs = (max_n + prm.tiles * ts::kP - 1) / (prm.tiles * ts::kP);
     const int grid = (int)std::min<int64_t>(pairs, num_sms(net->device));
-    ts::tower_ts_kernel<kEpiWarps><<<grid, (ts::kLoaderWarps + 2 + kEpiWarps) * 32, ts::kSmem, stream>>>(prm);
+    ts::tower_ts_kernel<kEpiWarps, kCrossFirst><<<grid, (ts::kLoaderWarps + 2 + kEpiWarps) * 32, ts::kSmem, stream>>>(prm);
     CK_CUDA(cudaGetLastError());
     return CK_OK;
 }
@@ -499,6 +589,7 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     static const int force_tiles = [] { const char *v = getenv("CK_TS_TILES"); return v ? atoi(v) : 0; }();
     prm.tiles = force_tiles == 1 || force_tiles == 2 ? force_tiles : (max_n <= (int64_t)ts::kP * num_sms(net->device) ? 1 : 2);
     prm.wts = (const uint4 *)net->d_wts; prm.blob = net->d_blob; prm.fold = net->d_scale;
+    prm.wts_cf = (const uint4 *)((const uint8_t *)net->d_wts + ts::kCopies * ts::kWtsBytes + 1024);
     prm.inv_scale = aux + 16;
     prm.plane5 = aux + 32;
     for (int i = 0; i < 8; ++i) prm.bias_off[i] = L.conv[i].bias;
@@ -506,7 +597,9 @@ int net_ts_tower(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int3
     prm.val1x1_k = L.val1x1.kernel; prm.val1x1_b = L.val1x1.bias;
     prm.pflat = d_pflat; prm.vconv = d_vconv;
     prm.range_flag = net->d_range_flag;
-    const int rc = launch_tower_ts<8>(net, prm, max_n, stream);
+    // CK_TS_ORDER=il selects the interleaved MMA order of round 1 (one chain of 216 MMAs per layer; A/B of the accuracy fix)
+    static const bool interleaved = [] { const char *v = getenv("CK_TS_ORDER"); return v && v[0] == 'i'; }();
+    const int rc = interleaved ? launch_tower_ts<8, false>(net, prm, max_n, stream) : launch_tower_ts<8, true>(net, prm, max_n, stream);
     if (rc != CK_OK) return rc;
     if (launches) *launches += 1;
     return CK_OK;

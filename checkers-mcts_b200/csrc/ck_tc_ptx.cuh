@@ -91,6 +91,21 @@ __device__ __forceinline__ void tc_kstep_ts_elect(uint32_t d_tmem, uint32_t a_tm
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_hi), "r"(lo_off), "r"(idesc), "r"(accumulate), "r"(bar) : "memory");
 }
+// Two MMAs on one weight slot, then the commit that frees it:  D (+)= A0*B0;  D += A1*B1;  commit -> bar
+// (a0 / a1: TMEM column addresses of the two 8-column operand halves of the slot, b0 / b1: shared-memory descriptors)
+__device__ __forceinline__ void tc_pair_ts_elect(uint32_t d_tmem, uint32_t a0, uint64_t b0, uint32_t a1, uint64_t b1, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e, t;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %5, p;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], %4, %5, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+        "}\n" ::"r"(d_tmem), "r"(a0), "l"(b0), "r"(a1), "l"(b1), "r"(idesc), "r"(accumulate), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
     asm volatile(
         "{\n"
