@@ -18,11 +18,13 @@ NET_TOL = 1e-5       # north_star: "within 1e-5 on policy/value logits given ide
 #   * any fp32 evaluation of these trained networks sits ~1.5e-5 from float64 on the logits (|logit| up to 15, nine layers
 #     of fp32 rounding): the fp32 CUDA-core path measures 1.2e-5 .. 1.5e-5, so 1e-5 on logits against float64 is beyond
 #     fp32 itself -- Keras' own fp32 result differs from float64 by as much;
-#   * the tensor-core path adds the tensor pipe's round-toward-zero accumulation (a systematic -5e-6 relative shrink,
-#     scripts/k3_error_probe.py, profiles/r2b_k3_error_probe.jsonl): logits 1.1e-4 .. 1.5e-4 absolute = 1e-5 RELATIVE to
-#     the largest logit; what model.predict returns and the search consumes -- softmax probabilities and the tanh value --
-#     are within 1e-5 / 1.5e-5.
-TOL = {"tc": dict(policy=1e-5, value=2e-5, logits=2.5e-4, value_pre=5e-5),
+#   * the tensor pipe rounds its accumulator toward zero after every MMA (scripts/k3_error_probe.py: the error is a
+#     systematic shrink).  With the round-1 interleaved order (one chain of 216 MMAs per layer, CK_TS_ORDER=il) the logits
+#     are 1.1e-4 .. 1.5e-4 off and the tanh value 1.4e-5; the product order issues the small cross terms first (72 MMAs at
+#     full magnitude): logits 5.4e-5 .. 5.7e-5 = 3.7e-6 RELATIVE to the largest logit, and what model.predict returns and
+#     the search consumes -- softmax probabilities and the tanh value -- within 4.1e-6 / 5.3e-6.
+TOL = {"tc": dict(policy=1e-5, value=1e-5, logits=1e-4, value_pre=2e-5),
+       "tc-interleaved": dict(policy=1e-5, value=2e-5, logits=2.5e-4, value_pre=5e-5),
        "simt": dict(policy=1e-5, value=1e-5, logits=3e-5, value_pre=1e-5)}
 
 
@@ -33,7 +35,7 @@ def lib():
     return L
 
 
-@pytest.mark.parametrize("variant", ["ts", "ts-one-tile", "ts-two-tiles", "ss", "ts-simt-heads", "simt"])
+@pytest.mark.parametrize("variant", ["ts", "ts-one-tile", "ts-two-tiles", "ts-interleaved", "ss", "ts-simt-heads", "simt"])
 def test_trained_weights_logits(variant):
     """every tower / heads variant on Model10 and Model5 (the tower is chosen once per process, hence a subprocess)"""
     env = dict(os.environ)
@@ -48,6 +50,9 @@ def test_trained_weights_logits(variant):
         env["CK_HEADS"] = "simt"
     elif variant == "simt":
         impl = "simt"
+    elif variant == "ts-interleaved":
+        env["CK_TS_ORDER"] = "il"
+    tol = TOL["tc-interleaved" if variant in ("ts-interleaved", "ss") else impl]
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_trained.py"), "--impl", impl, "--tol", "1.0"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -55,8 +60,8 @@ def test_trained_weights_logits(variant):
     assert len(lines) == 2
     for l in lines:
         assert l["max_abs_logit"] > 5                                              # trained logits are not tiny
-        for k, tol in TOL[impl].items():
-            assert l["max_err"][k] < tol, (variant, l["model"], k, l["max_err"][k], tol)
+        for k, t in tol.items():
+            assert l["max_err"][k] < t, (variant, l["model"], k, l["max_err"][k], t)
         assert l["max_err"]["logits"] < 1.5e-5 * l["max_abs_logit"] + 3e-5         # relative to the largest logit
 
 
