@@ -141,8 +141,7 @@ movegen_emit_kernel(const uint4 *__restrict__ pos, int64_t n, ck_pos *__restrict
     __shared__ uint32_t s_warp_tot[kCsrTile / 32];
     __shared__ uint4 s_pos[kCsrTile], s_hop[kCsrTile];    // position; its hop sets (make_child_fast)
     __shared__ uint32_t s_off[kCsrTile];                  // first successor inside the tile | jump flag << 31
-    __shared__ uint8_t s_move[kCsrTile * CK_MAX_CHILDREN]; // the tile's move list: source square | direction << 5
-    __shared__ uint8_t s_owner[kCsrTile * CK_MAX_CHILDREN]; // and the position (thread) each move belongs to
+    __shared__ uint16_t s_move[kCsrTile * CK_MAX_CHILDREN]; // the tile's move list: source square | direction << 5 | owner thread << 8
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * kCsrTile + tid;
     ck_pos p;
@@ -171,30 +170,42 @@ movegen_emit_kernel(const uint4 *__restrict__ pos, int64_t n, ck_pos *__restrict
         s_hop[tid] = make_uint4(J[0], J[1], J[2], J[3]);
         s_off[tid] = loc | (jump ? 0x80000000u : 0u);
         const uint32_t u0 = jump ? mask[4] : mask[0], u1 = jump ? mask[5] : mask[1], u2 = jump ? mask[6] : mask[2], u3 = jump ? mask[7] : mask[3];
-        const uint32_t any = u0 | u1 | u2 | u3;
+        // The reference's order with the direction slots fixed per position up front instead of selected
+        // per move: men in ascending square order, each with its two forward directions (right then left for plain moves,
+        // ydir = -1 then +1 for hops); then kings likewise with UL,UR,BL,BR (moves) or UL,BL,UR,BR (hops).  One 16-bit
+        // store per move: square | direction << 5 | owner << 8.  (ncu source view, profiles/r2k: this loop was 40 % of the
+        // kernel's instructions with per-move direction selects and two byte stores.)
+        const bool p0 = sd.player == 0;
+        const int fwd = p0 ? 2 : 0;
+        const uint32_t f_lo = p0 ? u2 : u0, f_hi = p0 ? u3 : u1;                 // forward-left / forward-right of this side
+        const uint32_t ma = (jump ? f_lo : f_hi) & ~sd.kings, mb = (jump ? f_hi : f_lo) & ~sd.kings;
+        const uint32_t da = (uint32_t)(jump ? fwd : fwd + 1) << 5, db = (uint32_t)(jump ? fwd + 1 : fwd) << 5;
+        const uint32_t own16 = (uint32_t)tid << 8;
         uint32_t m = loc;
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool king = pass == 1;
-            for (uint32_t rem = any & (king ? sd.kings : ~sd.kings); rem; rem &= rem - 1) {
-                const int s = ffs32(rem);
-                const int nd = king ? 4 : 2;
-                for (int q = 0; q < nd; ++q) {
-                    const int d = order_dir(king, jump, sd.player, q);
-                    const uint32_t ud = d == 0 ? u0 : d == 1 ? u1 : d == 2 ? u2 : u3;       // selects, not an indexed (local-memory) array
-                    if ((ud >> s) & 1u) { s_move[m] = (uint8_t)(s | (d << 5)); s_owner[m] = (uint8_t)tid; ++m; }
-                }
-            }
+        for (uint32_t rem = ma | mb; rem; rem &= rem - 1) {
+            const uint32_t s = (uint32_t)ffs32(rem);
+            if ((ma >> s) & 1u) s_move[m++] = (uint16_t)(s | da | own16);
+            if ((mb >> s) & 1u) s_move[m++] = (uint16_t)(s | db | own16);
+        }
+        const uint32_t k0 = u0 & sd.kings, k1 = (jump ? u2 : u1) & sd.kings, k2 = (jump ? u1 : u2) & sd.kings, k3 = u3 & sd.kings;
+        const uint32_t d1 = (uint32_t)(jump ? 2 : 1) << 5, d2 = (uint32_t)(jump ? 1 : 2) << 5;
+        for (uint32_t rem = k0 | k1 | k2 | k3; rem; rem &= rem - 1) {
+            const uint32_t s = (uint32_t)ffs32(rem);
+            if ((k0 >> s) & 1u) s_move[m++] = (uint16_t)(s | own16);
+            if ((k1 >> s) & 1u) s_move[m++] = (uint16_t)(s | d1 | own16);
+            if ((k2 >> s) & 1u) s_move[m++] = (uint16_t)(s | d2 | own16);
+            if ((k3 >> s) & 1u) s_move[m++] = (uint16_t)(s | (3u << 5) | own16);
         }
     }
     __syncthreads();
     for (uint32_t c = tid; c < tile_total; c += kCsrTile) {
-        const int lo = s_owner[c];
+        const uint32_t mv = s_move[c];
+        const int lo = (int)(mv >> 8);
         const uint4 pv = s_pos[lo], hv = s_hop[lo];
         ck_pos par;
         par.p1 = pv.x; par.p2 = pv.y; par.k = pv.z; par.meta = pv.w;
         const uint32_t J[4] = {hv.x, hv.y, hv.z, hv.w};
-        const uint32_t mv = s_move[c];
-        const ck_pos ch = make_child_fast(par, side_of(par), J, (int)(mv & 31u), (int)(mv >> 5), (s_off[lo] >> 31) != 0);
+        const ck_pos ch = make_child_fast(par, side_of(par), J, (int)(mv & 31u), (int)((mv >> 5) & 7u), (s_off[lo] >> 31) != 0);
         if ((unsigned long long)base + c < child_cap) reinterpret_cast<uint4 *>(children)[base + c] = make_uint4(ch.p1, ch.p2, ch.k, ch.meta);
     }
 }
