@@ -9,8 +9,9 @@ Dirichlet(alpha=1, eps=0.25) at every node, tau=1 with decay, TERMINATE_CNT=200,
 are refilled when their game ends.  One "step" = 400 lock-step rounds (tree kernel + batched network evaluation).
 
 Steady state: the slots are desynchronised by a warm start (the first game of slot i plays its first hash(i) mod 140 plies
-at 8 sims/move, everything after that at 400) and an untimed pre-roll that takes every slot past those plies, so the
-timed region sees full-budget games at every stage, finishing games included, instead of 4096 openings in lock step.  Then 2K steps alternate:
+at 8 sims/move, everything after that at 400) and an untimed pre-roll of about one game length at full budget, so the
+timed region sees games at every stage with trees and evaluation caches as deep as in a long run, finishing games
+included, instead of 4096 openings in lock step.  Then 2K steps alternate:
   even steps -> `value`: simulations / device time (CUDA events on the engine's stream), inputs resident in HBM;
   odd steps  -> `e2e`: the same loop through the host-buffer C ABI, wall clock: the weight blob goes up from pinned host
                 memory (H2D), the step runs, the finished games' records and results come back (D2H).
@@ -42,7 +43,7 @@ BUDGET = 400
 ROUNDS_PER_STEP = 400
 PREROLL_BUDGET = 8            # sims/move of the opening plies a slot's first game plays before full-budget play (warm start)
 PREROLL_PLIES = 140           # slot i does that for hash(i) mod 140 plies: stages spread over a typical game length
-PREROLL_ROUNDS = 2400         # untimed rounds: every slot past its warm-start plies and a few full-budget moves into its game
+PREROLL_ROUNDS = 24000        # untimed rounds (~28 s): about one game length at full budget, so trees and evaluation caches are as deep as in a long run
 REF_PLIES = 2                 # plies per game of a reference-arm sample (the reference's TERMINATE_CNT knob)
 TOWER_FLOP_PER_POS = 2 * (9 * 14 * 128 * 64 + 7 * 9 * 128 * 128 * 64 + 128 * 8 * 64)   # 134,316,032: the eight 3x3 convs + the policy conv1x1 the tower kernel evaluates
 NET_FLOP_PER_POS = 134865024                                               # SURVEY 8(d), whole network
@@ -283,7 +284,7 @@ def pipeline_e2e(dev, rank, world, n_games, num_cpus):
         return {"value": st["sims"] / wall, "unit": UNIT, "call": "generate_Checkers_data(selfplay_kwargs, mcts_kwargs).generate_data()",
                 "games": n_games, "workers_NUM_CPUS": num_cpus, "wall_s": wall, "gpu_s": st["gpu_ms"] / 1e3,
                 "host_s_after_gpu": gen.host_seconds, "host_share_of_gpu_time": gen.host_seconds / max(st["gpu_ms"] / 1e3, 1e-9),
-                "sims": st["sims"], "games_per_sec": n_games / wall, "records": gen.n_records, "pickle_bytes": nbytes, "files": len(files)}
+                "sims": st["sims"], "games_per_sec": n_games / wall, "plies_per_game": st["moves"] / max(n_games, 1), "records": gen.n_records, "pickle_bytes": nbytes, "files": len(files)}
     finally:
         os.chdir(cwd)
         shutil.rmtree(work, ignore_errors=True)
@@ -369,11 +370,13 @@ def run_ours(args, rank, world, local_rank):
     e = dict(sims=0, h2d=0, d2h=0, ms=0.0, launches=0, games=0, records=0)
     barrier()
     t0 = time.time()
-    for _ in range(args.steps):
+    def device_step():
         st = eng.run(args.rounds)                                           # device-resident step
         for k in keys:
             agg[k] += st[k]
         torch.cuda.synchronize()
+
+    def e2e_step():
         s0 = time.time()                                                    # end-to-end step through host buffers
         weights.copy_(pinned, non_blocking=False)                           # H2D: this step's input (the weights)
         net.set_weights_device(weights.data_ptr(), weights.numel())
@@ -384,6 +387,10 @@ def run_ours(args, rank, world, local_rank):
         e["sims"] += st["sims"]; e["launches"] += st["kernel_launches"]; e["games"] += st["games_finished"]; e["records"] += nrec
         e["h2d"] += blob.nbytes
         e["d2h"] += nrec * L.RECORD_DTYPE.itemsize + n_games * L.GAME_DTYPE.itemsize
+
+    for i in range(args.steps):                  # the order flips every step, so a slow drift of the game mix cancels between the two
+        for fn in ((device_step, e2e_step) if i % 2 == 0 else (e2e_step, device_step)):
+            fn()
     barrier()
     wall = time.time() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -444,6 +451,9 @@ def run_ours(args, rank, world, local_rank):
     line["games_finished"] = games
     line["games_per_sec"] = games / (gpu_ms / 1000.0)
     line["games_per_sec_est"] = (moves / (gpu_ms / 1000.0)) / 150.0      # at the ~150 plies/game BASELINE.md assumes
+    if pipe is not None and pipe.get("plies_per_game"):
+        # stationary rate: moves/s over the mean length of complete games (the e2e_pipeline batch, every game played to its end)
+        line["games_per_sec_at_mean_length"] = (moves / (gpu_ms / 1000.0)) / pipe["plies_per_game"]
     line["e2e"] = {"value": e2e_sims / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": e["h2d"] // max(args.steps, 1),
                    "d2h_bytes_per_step": e["d2h"] // max(args.steps, 1), "games_per_sec": e2e_games / (e2e_ms / 1000.0),
                    "games_finished": e2e_games, "how": "alternates with the device-timed steps; wall clock of H2D weights + 400 rounds + D2H records"}

@@ -1209,6 +1209,12 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         int want = cfg->eval_cache_entries > 0 ? cfg->eval_cache_entries : 16384;
         int ent = 16;
         while (ent < want && ent < (1 << 20)) ent *= 2;
+        if (cfg->eval_cache_entries == 0) {
+            // the default yields to the trees: at most a quarter of the free HBM (16384 entries x 65536 slots would be 137 GB)
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                while (ent > 256 && (size_t)cfg->n_slots * ent * kCacheU4 * sizeof(uint4) > free_b / 4) ent /= 2;
+        }
         d.cache_entries = ent;
         d.cache_game_tag = (cfg->evaluator == CK_EVAL_HASH_SALTED || cfg->evaluator_p2 == CK_EVAL_HASH_SALTED) ? 1 : 0;
     }
