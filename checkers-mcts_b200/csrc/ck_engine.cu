@@ -55,10 +55,12 @@ struct Slot {
 
 struct Counters {
     unsigned long long games_finished, moves, nodes, compactions;
-    int32_t next_game, error, halted, active;
-    int32_t batch_count[2];
-    int32_t deferred;        // leaves that asked for a batch row beyond leaf_cap this round (they ask again next round)
-    int32_t leaf_cap;        // rows the evaluator batch of this round may hold (round_begin_kernel)
+    int32_t next_game, error, halted, pad0;
+    // per evaluator batch (index = network in an arena, slot group in overlapped self-play, else 0):
+    int32_t active[2];       // slots that still have work after this round
+    int32_t batch_count[2];  // leaves staged this round
+    int32_t deferred[2];     // leaves that asked for a batch row beyond leaf_cap this round (they ask again next round)
+    int32_t leaf_cap[2];     // rows the evaluator batch of this round may hold (round_begin_kernel)
 };
 
 struct EngineDev {
@@ -84,6 +86,10 @@ struct EngineDev {
     int32_t cache_game_tag;      // 1: the evaluator depends on the game (salted stubs), so entries are tagged with it
     int32_t wave;                // positions one full wave of the tower evaluates (tiles x positions per tile x SMs); 0: no batch shaping
     int32_t wave_slack10;        // the batch is cut back to whole waves while the excess is below wave_slack10 / 10 of a wave
+    // overlapped self-play: the slots form two groups; while the tower evaluates the leaves of one group the tree
+    // kernel of the other runs next to it on the same SMs.  Per launch: which group, and its slot range.
+    int32_t groups;              // 1 or 2
+    int32_t grp, slot0, slot_n;
 };
 
 // ---- small device helpers --------------------------------------------------------------
@@ -135,7 +141,7 @@ __device__ __forceinline__ uint64_t game_key(const EngineDev &E, int local) {
     return mix64(E.cfg.seed ^ mix64((uint64_t)(uint32_t)global_game(E, local) + 0x51ED270B1ull));
 }
 __device__ __forceinline__ int net_of(const EngineDev &E, int local_game, int player) {
-    if (!E.cfg.arena) return 0;
+    if (!E.cfg.arena) return E.grp;                 // evaluator batch index: the slot group (0 unless overlapped)
     const int p1_net = global_game(E, local_game) < E.arena_half ? 0 : 1;   // training_pipeline.py:523-528
     return player == 0 ? p1_net : 1 - p1_net;
 }
@@ -294,9 +300,9 @@ __device__ void stage_leaf(const WarpCtx &c, int leaf, int depth) {
         const int net = net_of(E, S.game, S.cur);
         if (E.wave > 0) {
             const int row = atomicAdd(&E.ctr->batch_count[net], 1);
-            if (row >= *(volatile int32_t *)&E.ctr->leaf_cap) {
+            if (row >= *(volatile int32_t *)&E.ctr->leaf_cap[net]) {
                 atomicSub(&E.ctr->batch_count[net], 1);
-                atomicAdd(&E.ctr->deferred, 1);
+                atomicAdd(&E.ctr->deferred[net], 1);
                 leaf = -1;
             } else {
                 S.pend_row = row;
@@ -859,7 +865,7 @@ __device__ bool play_move(const WarpCtx &c) {
         ck_game_result &r = E.results[S.game];
         r.game = gg; r.outcome = outcome; r.move_count = S.move_count; r.terminated = terminated ? 1 : 0;
         r.n_records = S.nrec; r.reroot_misses = S.misses;
-        r.p1_net = net_of(E, S.game, 0); r.reserved = 0;
+        r.p1_net = E.cfg.arena ? net_of(E, S.game, 0) : 0; r.reserved = 0;
         r.sims = S.tot_sims - S.g_sims0; r.nn_evals = S.tot_evals - S.g_evals0;
         __threadfence();
         atomicAdd(&E.ctr->games_finished, 1ull);
@@ -875,13 +881,18 @@ __device__ bool play_move(const WarpCtx &c) {
 #ifndef CK_TREE_OCC
 #define CK_TREE_OCC 5
 #endif
-template <bool kUct>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, CK_TREE_OCC)
+#ifndef CK_OVERLAP_DEFAULT
+#define CK_OVERLAP_DEFAULT 0
+#endif
+// kWarps = 4: the stand-alone launch.  kWarps = 1: the overlapped launch -- one-warp blocks (3 K registers) fit next to a
+// resident tower CTA (576 threads x 96 registers leave 10 K of the SM's 64 K), three per SM.
+template <bool kUct, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, kWarps == 4 ? CK_TREE_OCC : 20)
 tree_step_kernel(const EngineDev E) {
-    __shared__ Slot s_slot[kWarpsPerBlock];
+    __shared__ Slot s_slot[kWarps];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kWarpsPerBlock + w;
-    if (slot >= E.n_slots) return;
+    const int slot = E.slot0 + blockIdx.x * kWarps + w;
+    if (slot >= E.slot0 + E.slot_n) return;
     Slot &S = s_slot[w];
     {
         const int *src = reinterpret_cast<const int *>(E.slots + slot);
@@ -922,7 +933,7 @@ tree_step_kernel(const EngineDev E) {
         __syncwarp();
         if (++term_iters >= max_term || ++chain >= max_chain) break;
     }
-    if (lane == 0 && S.game >= 0 && S.phase != PH_HALT) atomicAdd(&E.ctr->active, 1);
+    if (lane == 0 && S.game >= 0 && S.phase != PH_HALT) atomicAdd(&E.ctr->active[E.grp], 1);
     __syncwarp();
     {
         int *dst = reinterpret_cast<int *>(E.slots + slot);
@@ -958,17 +969,21 @@ __global__ void __launch_bounds__(32) manual_compact_kernel(const EngineDev E) {
 __global__ void round_begin_kernel(const EngineDev E) {
     Counters *c = E.ctr;
     if (threadIdx.x == 0) {
-        int cap = 0x7FFFFFFF;
-        if (E.wave > 0) {
-            // a leaf that waits costs its slot a whole evaluate-then-chain cycle (~2.4 simulations at cfg2), a wave iteration
-            // saved is worth ~590 of them: cutting the batch back pays while the excess is below ~0.5 wave (measured
-            // break-even, profiles/r2e_steady_sweep.jsonl); applied below 0.3 wave
-            const int asked = c->batch_count[0] + c->deferred;       // previous round
-            const int full = asked / E.wave * E.wave;
-            if (full >= E.wave && (asked - full) * 10 < E.wave_slack10 * E.wave) cap = full;
+        const int nb = E.cfg.arena ? 2 : 1;                  // arena: both networks' batches; otherwise this launch's group
+        for (int i = 0; i < nb; ++i) {
+            const int k = E.cfg.arena ? i : E.grp;
+            int cap = 0x7FFFFFFF;
+            if (E.wave > 0) {
+                // a leaf that waits costs its slot a whole evaluate-then-chain cycle (~2.4 simulations at cfg2), a wave iteration
+                // saved is worth ~590 of them: cutting the batch back pays while the excess is below ~0.5 wave (measured
+                // break-even, profiles/r2e_steady_sweep.jsonl); applied below 0.3 wave
+                const int asked = c->batch_count[k] + c->deferred[k];       // previous round of this group
+                const int full = asked / E.wave * E.wave;
+                if (full >= E.wave && (asked - full) * 10 < E.wave_slack10 * E.wave) cap = full;
+            }
+            c->leaf_cap[k] = cap;
+            c->active[k] = 0; c->batch_count[k] = 0; c->deferred[k] = 0;
         }
-        c->leaf_cap = cap;
-        c->active = 0; c->batch_count[0] = 0; c->batch_count[1] = 0; c->deferred = 0;
     }
 }
 
@@ -1117,7 +1132,10 @@ struct ck_engine {
     ck_net *net[2] = {nullptr, nullptr};
     uint64_t net_gen[2] = {0, 0};       // weights generation the evaluation cache was filled under
     cudaStream_t stream = nullptr;
-    cudaStream_t stream_b = nullptr;    // arena: the second network evaluates next to the first one
+    cudaStream_t stream_b = nullptr;    // arena: the second network evaluates next to the first one; overlapped self-play: the tree stream
+    cudaEvent_t ev_tree[2] = {nullptr, nullptr}, ev_eval[2] = {nullptr, nullptr};   // overlapped self-play: per slot group
+    cudaEvent_t ev_fork_run = nullptr;
+    bool eval_pending[2] = {false, false};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> prof_ev;   // 3 per round in profile mode: before eval, after tower, after eval
     std::vector<char> fetched;          // per local game: records already handed out by ck_records_fetch_new
@@ -1140,6 +1158,8 @@ static void engine_free(ck_engine *e) {
     cudaFree(d.cache);
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->stream_b) cudaStreamDestroy(e->stream_b);
+    for (int k = 0; k < 2; ++k) { if (e->ev_tree[k]) cudaEventDestroy(e->ev_tree[k]); if (e->ev_eval[k]) cudaEventDestroy(e->ev_eval[k]); }
+    if (e->ev_fork_run) cudaEventDestroy(e->ev_fork_run);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1229,8 +1249,25 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         if (shape_env > 1) d.wave = cfg->arena ? 0 : shape_env;
         else d.wave = (shape_env != 0 && cfg->evaluator == CK_EVAL_NET && !cfg->arena && cfg->n_slots >= 2 * wave) ? wave : 0;
     }
+    // Overlapped self-play: two slot groups, the tree kernel of one runs next to the tower of the other (CK_OVERLAP=0|1
+    // overrides).  Needs two full-size batches of tower waves to pay: see DESIGN.md section 5.
+    {
+        static const int ov_env = getenv("CK_OVERLAP") ? atoi(getenv("CK_OVERLAP")) : -1;
+        const int wave = 4 * num_sms(cfg->device);
+        const bool can = cfg->evaluator == CK_EVAL_NET && !cfg->arena && cfg->n_slots >= 4 * wave;
+        d.groups = (can && (ov_env > 0 || (ov_env < 0 && CK_OVERLAP_DEFAULT))) ? 2 : 1;
+    }
+    d.grp = 0; d.slot0 = 0; d.slot_n = cfg->n_slots;
     CK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK_E(cudaEventCreate(&e->ev0)); CK_E(cudaEventCreate(&e->ev1));
+    if (d.groups == 2) {
+        CK_E(cudaStreamCreateWithFlags(&e->stream_b, cudaStreamNonBlocking));
+        CK_E(cudaEventCreateWithFlags(&e->ev_fork_run, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CK_E(cudaEventCreateWithFlags(&e->ev_tree[k], cudaEventDisableTiming));
+            CK_E(cudaEventCreateWithFlags(&e->ev_eval[k], cudaEventDisableTiming));
+        }
+    }
     if (cfg->arena) {
         CK_E(cudaStreamCreateWithFlags(&e->stream_b, cudaStreamNonBlocking));
         CK_E(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -1244,7 +1281,7 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     CK_E(cudaMalloc(&d.slots, (size_t)d.n_slots * sizeof(Slot)));
     CK_E(cudaMalloc(&d.ctr, sizeof(Counters)));
     CK_E(cudaMemset(d.ctr, 0, sizeof(Counters)));
-    for (int k = 0; k < (cfg->arena ? 2 : 1); ++k) {
+    for (int k = 0; k < ((cfg->arena || d.groups == 2) ? 2 : 1); ++k) {
         CK_E(cudaMalloc(&d.leaves[k], (size_t)d.n_slots * sizeof(ck_leaf)));
         CK_E(cudaMalloc(&d.policy[k], (size_t)d.n_slots * CK_POLICY_SIZE * sizeof(float)));
         CK_E(cudaMalloc(&d.value[k], (size_t)d.n_slots * sizeof(float)));
@@ -1368,6 +1405,7 @@ int ck_engine_begin(ck_engine *e, int64_t n_games) {
     e->fetched.assign((size_t)n_games, 0);
     int rc = engine_reset_slots(e, 0);
     if (rc != CK_OK) return rc;
+    e->eval_pending[0] = e->eval_pending[1] = false;
     e->begun = true;
     return CK_OK;
 }
@@ -1376,8 +1414,36 @@ static void launch_tree_step(ck_engine *e) {
     EngineDev &d = e->dev;
     const int grid = (d.n_slots + kWarpsPerBlock - 1) / kWarpsPerBlock;
     d.round += 1;
-    if (d.uct) tree_step_kernel<true><<<grid, kWarpsPerBlock * 32, 0, e->stream>>>(d);
-    else tree_step_kernel<false><<<grid, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+    d.grp = 0; d.slot0 = 0; d.slot_n = d.n_slots;
+    if (d.uct) tree_step_kernel<true, kWarpsPerBlock><<<grid, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+    else tree_step_kernel<false, kWarpsPerBlock><<<grid, kWarpsPerBlock * 32, 0, e->stream>>>(d);
+}
+
+// Overlapped self-play (two slot groups): one round of group g = [tree stream] wait for the group's previous
+// evaluation -> round_begin -> tree_step of its slots (one-warp blocks: they fit next to the resident tower CTAs of the
+// OTHER group's evaluation) -> [main stream] wait for that -> tower + heads of the group's leaves.  Enqueued g = 0, 1, 0, 1,
+// ...: the tree work of one group runs while the tensor pipe evaluates the other.
+static int engine_round_group(ck_engine *e, int g, int *launches, cudaEvent_t *prof = nullptr) {
+    EngineDev &d = e->dev;
+    const int half = d.n_slots / 2;
+    EngineDev k = d;
+    k.grp = g; k.slot0 = g ? half : 0; k.slot_n = g ? d.n_slots - half : half;
+    cudaStream_t ts = e->stream_b;
+    if (e->eval_pending[g]) CK_CUDA(cudaStreamWaitEvent(ts, e->ev_eval[g], 0));
+    round_begin_kernel<<<1, 32, 0, ts>>>(k);
+    tree_step_kernel<false, 1><<<k.slot_n, 32, 0, ts>>>(k);
+    CK_CUDA(cudaGetLastError());
+    CK_CUDA(cudaEventRecord(e->ev_tree[g], ts));
+    CK_CUDA(cudaStreamWaitEvent(e->stream, e->ev_tree[g], 0));
+    if (prof) { CK_CUDA(cudaEventRecord(prof[0], e->stream)); e->net[0]->ev_after_tower = prof[1]; }
+    int rc = net_forward_rows(e->net[0], d.leaves[g], k.slot_n, &d.ctr->batch_count[g], d.policy[g], d.value[g], e->stream, launches, g);
+    if (prof) e->net[0]->ev_after_tower = nullptr;
+    if (rc != CK_OK) return rc;
+    if (prof) CK_CUDA(cudaEventRecord(prof[2], e->stream));
+    CK_CUDA(cudaEventRecord(e->ev_eval[g], e->stream));
+    e->eval_pending[g] = true;
+    if (launches) *launches += 2;
+    return CK_OK;
 }
 
 static int engine_eval(ck_engine *e, int *launches) {
@@ -1424,6 +1490,10 @@ static int engine_eval(ck_engine *e, int *launches) {
 // One lock-step round = tree kernel + evaluation of the staged leaves.
 static int engine_round(ck_engine *e, int *launches) {
     EngineDev &d = e->dev;
+    if (d.groups == 2) {
+        int rc = engine_round_group(e, 0, launches);
+        return rc != CK_OK ? rc : engine_round_group(e, 1, launches);
+    }
     round_begin_kernel<<<1, 32, 0, e->stream>>>(d);      // batch cap of the round, counters to zero
     launch_tree_step(e);
     if (launches) *launches += 2;
@@ -1432,6 +1502,7 @@ static int engine_round(ck_engine *e, int *launches) {
 }
 
 static int engine_poll(ck_engine *e) {
+    if (e->dev.groups == 2) CK_CUDA(cudaStreamSynchronize(e->stream_b));       // the tree stream runs ahead of the main stream's waits
     CK_CUDA(cudaMemcpyAsync(e->h_ctr, e->dev.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
     int32_t *h_range = reinterpret_cast<int32_t *>(e->h_ctr + 1);
     h_range[0] = h_range[1] = 0;
@@ -1469,13 +1540,23 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
     CK_CUDA(cudaEventRecord(e->ev0, e->stream));
     int64_t steps = 0;
     const int check = 16;
-    if (e->profile && e->prof_ev.size() < (size_t)3 * check) {
-        while (e->prof_ev.size() < (size_t)3 * check) { cudaEvent_t ev; CK_CUDA(cudaEventCreate(&ev)); e->prof_ev.push_back(ev); }
+    const int per_round_ev = 3 * d.groups;               // before the evaluation, after the tower, after the heads -- per slot group
+    if (e->profile && e->prof_ev.size() < (size_t)per_round_ev * check) {
+        while (e->prof_ev.size() < (size_t)per_round_ev * check) { cudaEvent_t ev; CK_CUDA(cudaEventCreate(&ev)); e->prof_ev.push_back(ev); }
+    }
+    if (d.groups == 2) {                                 // the tree stream starts after whatever the main stream did before this call
+        CK_CUDA(cudaEventRecord(e->ev_fork_run, e->stream));
+        CK_CUDA(cudaStreamWaitEvent(e->stream_b, e->ev_fork_run, 0));
     }
     for (;;) {
         const int64_t chunk = n_steps > 0 ? std::min<int64_t>(check, n_steps - steps) : check;
         for (int64_t i = 0; i < chunk; ++i) {
-            if (e->profile) {
+            if (e->profile && d.groups == 2) {
+                for (int g = 0; g < 2; ++g) {
+                    rc = engine_round_group(e, g, &launches, &e->prof_ev[6 * i + 3 * g]);
+                    if (rc != CK_OK) return rc;
+                }
+            } else if (e->profile) {
                 round_begin_kernel<<<1, 32, 0, e->stream>>>(d);
                 launch_tree_step(e);
                 launches += 2;
@@ -1494,7 +1575,7 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
         rc = engine_poll(e);
         if (rc != CK_OK) return rc;
         if (e->profile) {
-            for (int64_t i = 0; i < chunk; ++i) {
+            for (int64_t i = 0; i < chunk * d.groups; ++i) {
                 float a = 0.f, b = 0.f;
                 cudaEventElapsedTime(&a, e->prof_ev[3 * i], e->prof_ev[3 * i + 2]);
                 if (d.cfg.evaluator == CK_EVAL_NET && cudaEventElapsedTime(&b, e->prof_ev[3 * i], e->prof_ev[3 * i + 1]) == cudaSuccess) tower_ms += b;
@@ -1503,7 +1584,7 @@ int ck_engine_run(ck_engine *e, int64_t n_steps, ck_run_stats *stats) {
             cudaGetLastError();
         }
         if (n_steps > 0 && steps >= n_steps) break;
-        if (n_steps <= 0 && e->h_ctr->active == 0 && e->h_ctr->batch_count[0] == 0 && e->h_ctr->batch_count[1] == 0) break;
+        if (n_steps <= 0 && e->h_ctr->active[0] + e->h_ctr->active[1] == 0 && e->h_ctr->batch_count[0] == 0 && e->h_ctr->batch_count[1] == 0) break;
         if (n_steps <= 0 && e->h_ctr->games_finished >= (unsigned long long)e->n_games) break;
     }
     CK_CUDA(cudaEventRecord(e->ev1, e->stream));
@@ -1735,7 +1816,7 @@ int ck_tree_search(ck_engine *e, int32_t sims) {
         for (int i = 0; i < 16; ++i) { rc = engine_round(e, nullptr); if (rc != CK_OK) return rc; }
         rc = engine_poll(e);
         if (rc != CK_OK) return rc;
-        if (e->h_ctr->active == 0) break;
+        if (e->h_ctr->active[0] + e->h_ctr->active[1] == 0) break;
     }
     return CK_OK;
 }

@@ -313,14 +313,16 @@ heads_kernel(const float *__restrict__ trunk, const float *__restrict__ pconv, i
 // ---- host side -----------------------------------------------------------------------------
 // scratch between the tower and the heads: per position 64 + 1024 floats on the fused path (value conv
 // output; policy features + logits), two full fp32 feature maps [128][64] on the cross-check paths
-int net_reserve(ck_net *net, int64_t n, bool full_maps) {
+int net_reserve(ck_net *net, int64_t n, bool full_maps, int lane) {
     const size_t per0 = full_maps ? (size_t)kC * 64 : 64, per1 = full_maps ? (size_t)kC * 64 : 1024;
-    if ((size_t)n * per0 <= net->act0_floats && (size_t)n * per1 <= net->act1_floats) return CK_OK;
-    cudaFree(net->d_act0); cudaFree(net->d_act1);
-    net->d_act0 = net->d_act1 = nullptr; net->act0_floats = net->act1_floats = 0;
-    CK_CUDA(cudaMalloc(&net->d_act0, (size_t)n * per0 * sizeof(float)));
-    CK_CUDA(cudaMalloc(&net->d_act1, (size_t)n * per1 * sizeof(float)));
-    net->act0_floats = (size_t)n * per0; net->act1_floats = (size_t)n * per1;
+    float *&a0 = lane ? net->d_act0b : net->d_act0, *&a1 = lane ? net->d_act1b : net->d_act1;
+    size_t &f0 = lane ? net->act0b_floats : net->act0_floats, &f1 = lane ? net->act1b_floats : net->act1_floats;
+    if ((size_t)n * per0 <= f0 && (size_t)n * per1 <= f1) return CK_OK;
+    cudaFree(a0); cudaFree(a1);
+    a0 = a1 = nullptr; f0 = f1 = 0;
+    CK_CUDA(cudaMalloc(&a0, (size_t)n * per0 * sizeof(float)));
+    CK_CUDA(cudaMalloc(&a1, (size_t)n * per1 * sizeof(float)));
+    f0 = (size_t)n * per0; f1 = (size_t)n * per1;
     return CK_OK;
 }
 
@@ -358,17 +360,17 @@ static int net_finish_weights(ck_net *net) {
 }
 
 int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
-                     float *d_policy, float *d_value, cudaStream_t stream, int *launches) {
+                     float *d_policy, float *d_value, cudaStream_t stream, int *launches, int lane) {
     if (!net->have_weights) return fail(CK_ERR_NO_NET, "ck_net: weights were never set");
     if (max_n <= 0) return CK_OK;
     static const bool tower_ss = [] { const char *v = getenv("CK_TOWER"); return v && v[0] == 's'; }();
-    int rc = net_reserve(net, max_n, net->impl == CK_NET_IMPL_SIMT || tower_ss);
+    int rc = net_reserve(net, max_n, net->impl == CK_NET_IMPL_SIMT || tower_ss, lane);
     if (rc != CK_OK) return rc;
     rc = ensure_constants(net->device);
     if (rc != CK_OK) return rc;
     const NetLayout L = net_layout();
     const float *blob = net->d_blob;
-    float *trunk = net->d_act0, *pconv = net->d_act1;
+    float *trunk = lane ? net->d_act0b : net->d_act0, *pconv = lane ? net->d_act1b : net->d_act1;
     int nl = 0;
     bool fused = false;
     if (net->impl == CK_NET_IMPL_SIMT) {
@@ -378,7 +380,7 @@ int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const 
             CK_CUDA(cudaFuncSetAttribute(conv3x3_simt_kernel<kC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));
             attr_done[net->device & 63] = true;
         }
-        float *a = net->d_act0, *b = net->d_act1;
+        float *a = trunk, *b = pconv;
         conv3x3_simt_kernel<14, true><<<(unsigned)max_n, 256, smem14, stream>>>(
             d_leaves, nullptr, n_dev, blob + L.conv[0].kernel, blob + L.conv[0].bias, net->d_scale + kScaleTower, a);
         ++nl;
@@ -481,7 +483,7 @@ void ck_net_destroy(ck_net *net) {
     if (!net) return;
     DeviceGuard g(net->device);
     cudaFree(net->d_blob); cudaFree(net->d_scale); cudaFree(net->d_wpack); cudaFree(net->d_wts); cudaFree(net->d_hpack);
-    cudaFree(net->d_act0); cudaFree(net->d_act1);
+    cudaFree(net->d_act0); cudaFree(net->d_act1); cudaFree(net->d_act0b); cudaFree(net->d_act1b);
     cudaFree(net->d_leaves); cudaFree(net->d_policy); cudaFree(net->d_value); cudaFree(net->d_range_flag); cudaFree(net->d_stage);
     delete net;
 }

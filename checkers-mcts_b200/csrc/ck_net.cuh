@@ -37,8 +37,11 @@ struct ck_net {
     void *d_hpack = nullptr;         // policy Dense(512) weights, split fp16, UMMA layout (ck_heads_tc.cu)
     void *d_wts = nullptr;           // split-fp16 weights in k-step order for the weights-in-TMEM tower (ck_net_ts.cu)
     // activation scratch, grown on demand
-    size_t act0_floats = 0, act1_floats = 0;
-    float *d_act0 = nullptr, *d_act1 = nullptr;   // tower -> heads scratch (net_reserve)
+    // tower -> heads scratch (net_reserve); two sets ("lanes") so that two batches of one network can be in flight at once
+    size_t act0_floats = 0, act1_floats = 0;      // lane 0 (also what ck_net_last_features reads)
+    float *d_act0 = nullptr, *d_act1 = nullptr;
+    size_t act0b_floats = 0, act1b_floats = 0;    // lane 1 (the second slot group of an overlapped engine)
+    float *d_act0b = nullptr, *d_act1b = nullptr;
     ck_leaf *d_leaves = nullptr;     // staging for host entry points
     float *d_policy = nullptr, *d_value = nullptr;
     int64_t io_cap = 0;
@@ -56,13 +59,13 @@ constexpr int kScaleVal1x1 = kScalePol1x1 + 16;       // 1 scale, 1 shift
 constexpr int kScaleValD1 = kScaleVal1x1 + 2;         // 64 scale, 64 shift
 constexpr int kScaleTotal = kScaleValD1 + 128;
 
-int net_reserve(ck_net *net, int64_t n, bool full_maps);
+int net_reserve(ck_net *net, int64_t n, bool full_maps, int lane = 0);
 // CK_ERR_NET_RANGE (and the flag cleared) if a tensor-core kernel of this net saw an activation beyond the split-fp16
 // range since the last check; synchronises the default stream's view of the flag with a blocking 4-byte copy
 int net_check_range(ck_net *net);
 // n_dev (optional): device pointer to the live row count; rows >= *n_dev are skipped
 int net_forward_rows(ck_net *net, const ck_leaf *d_leaves, int64_t max_n, const int32_t *n_dev,
-                     float *d_policy, float *d_value, cudaStream_t stream, int *launches);
+                     float *d_policy, float *d_value, cudaStream_t stream, int *launches, int lane = 0);
 // tcgen05 tower (ck_net_tc.cu): leaves -> trunk (conv6 output) and policy-conv output,
 // both fp32 [n][128][64]
 int net_tc_prepare(ck_net *net);
