@@ -442,6 +442,35 @@ def test_batch_shaping_is_transparent():
     assert k == len(a[0])
 
 
+def test_overlapped_groups_are_transparent():
+    """CK_OVERLAP=1: the slots form two groups and the tree kernel of one runs on a second stream next to the tower of the
+    other (one-warp blocks, per-group batches and counters).  Same records, bit for bit, as the single-stream engine
+    (network evaluator, noise and temperature on, 2560 slots = the smallest size that enables the option)."""
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import sys, json; sys.path[:0] = %r\n"
+        "import numpy as np\n"
+        "from ckb200 import lib, net as N\n"
+        "net = lib.Net(0); net.set_weights(N.random_init_blob(0))\n"
+        "eng = lib.Engine(lib.make_cfg(n_slots=2560, budget=60, training=True, terminate_cnt=4, evaluator='net', uct_c=4.0, alpha=1.0,\n"
+        "                              epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10, seed=21))\n"
+        "eng.set_net(0, net)\n"
+        "st = eng.selfplay(2560)\n"
+        "r = eng.records(); r = r[np.lexsort((r['ply'], r['game']))]\n"
+        "np.save(sys.argv[1], r); print(json.dumps(dict(sims=st['sims'], evals=st['nn_evals'], games=st['games_finished'])))\n") % ([ROOT, PKG],)
+    outs = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for ov in ("0", "1"):
+            fn = os.path.join(tmp, "r%s.npy" % ov)
+            r = subprocess.run([sys.executable, "-c", code, fn], env=dict(os.environ, CK_OVERLAP=ov), capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            outs[ov] = (np.load(fn), json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs["0"][1] == outs["1"][1] and outs["0"][1]["games"] == 2560
+    assert outs["0"][0].tobytes() == outs["1"][0].tobytes()
+
+
 def test_packed_records_equal_full_records(lib):
     """device-side packing (ck_records_pack_device / ck_records_fetch_packed: 40-byte headers + one word per child) loses
     nothing: unpacked on the host it is bit-identical to ck_records_fetch, also with unfinished games in the store, and
