@@ -60,7 +60,11 @@ __host__ __device__ constexpr int cf_slots(int ksteps) { return ksteps + (ksteps
 constexpr int kGcf = cf_slots(kKSteps0) + 7 * cf_slots(kKStepsL) + cf_slots(kKSteps8);   // 14 + 7 * 108 + 12 = 782 slot images
 constexpr int kNS = 16;                             // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
-constexpr int kLoaderWarps = 8;                     // two sets of four (one warp per TMEM lane quadrant)
+#ifndef CK_TS_LOADER_SETS
+#define CK_TS_LOADER_SETS 2
+#endif
+constexpr int kLoaderSets = CK_TS_LOADER_SETS;      // sets of four warps (one warp per TMEM lane quadrant) that take turns on the slot groups
+constexpr int kLoaderWarps = 4 * kLoaderSets;
 constexpr int kLoadGroup = 4;                       // k-steps a loader warp fetches per batch
 constexpr float kActScale = 16.0f;                  // activations are stored as a * 2^4
 #ifndef CK_POLL_NS
@@ -158,7 +162,7 @@ tower_ts_kernel(const TowerParams prm) {
         const uint4 *src = (kCrossFirst ? prm.wts_cf : prm.wts + (size_t)(blockIdx.x % kCopies) * (kWtsBytes / 16)) + (quad * 32 + lane);
         const uint32_t t_w = ((uint32_t)(quad * 32) << 16) + kWCol0;
         uint32_t r[kLoadGroup][16];
-        for (uint32_t base = (uint32_t)(set * kLoadGroup); base < total; base += 2 * kLoadGroup) {
+        for (uint32_t base = (uint32_t)(set * kLoadGroup); base < total; base += kLoaderSets * kLoadGroup) {
 #pragma unroll
             for (int j = 0; j < kLoadGroup; ++j) {
                 const uint32_t g = (base + j) % (uint32_t)kGs;           // reads past `total` stay inside the stream
