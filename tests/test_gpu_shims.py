@@ -276,3 +276,35 @@ def test_final_evaluation_round_robin(mods, tmp_path, monkeypatch):
     assert fn.startswith("data/final_eval/Checkers_Final_Evaluation_") and "Total" in txt
     with pytest.raises(ValueError):
         T.final_evaluation([0, 5], dict(NUM_CPUS=1), MCTS_KW)
+
+
+def test_generate_data_pooled_writers_equal_inline_conversion(mods, tmp_path, monkeypatch):
+    """generate_data() at a size where the per-worker pickles are written by the process pool (ckb200.records.
+    save_reference_pickles: > 20 000 records): every file loads as the reference's list format and equals the
+    inline conversion of the same engine records, worker by worker."""
+    from ckb200 import lib as L
+    from ckb200 import records as R
+    _, _, T = mods
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/training_data")
+    sp = dict(NUM_SELFPLAY_GAMES=80, TRAINING_ITERATION=2, TERMINATE_CNT=110, NUM_CPUS=4, NN_FN='stub:hash_salted', SEED=31)
+    mk = dict(MCTS_KW, BUDGET=6, TRAINING=True, DIRICHLET_EPSILON=0.25, TEMPERATURE_TAU=1.0, TEMPERATURE_DECAY=0.1, TEMP_DECAY_DELAY=10)
+    gen = T.generate_Checkers_data(sp, mk)
+    fns = gen.generate_data()
+    assert len(fns) == 4 and gen.n_records > 20000
+    eng = L.Engine(L.make_cfg(n_slots=320, budget=6, training=True, terminate_cnt=110, evaluator="hash_salted", seed=31, uct_c=MCTS_KW['UCT_C'],
+                              alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10))
+    eng.selfplay(320)
+    recs = eng.records()
+    eng.close()
+    recs = recs[np.argsort(recs["game"], kind="stable")]
+    assert len(recs) == gen.n_records
+    total = 0
+    for p, fn in enumerate(fns):
+        data = pickle.load(open(fn, "rb"))
+        want = R.to_reference_list(recs[(recs["game"] >= 80 * p) & (recs["game"] < 80 * (p + 1))])
+        assert len(data) == len(want) > 0
+        for a, b in zip(data[:50] + data[-50:], want[:50] + want[-50:]):
+            assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2] and a[3] == b[3] and type(a[2]) is type(b[2])
+        total += len(data)
+    assert total == gen.n_records
