@@ -122,6 +122,25 @@ class _File(object):
                 return self.group_entries(struct.unpack_from("<Q", body, 0)[0], struct.unpack_from("<Q", body, 8)[0])
         return []
 
+    def dataset_extent(self, entry):
+        """-> (file offset, nbytes, shape, dtype) of a contiguous little-endian float dataset, else None"""
+        shape = dtype = addr = size = None
+        for mtype, body in self.messages(entry["header"]):
+            if mtype == 0x1:
+                ver, rank = body[0], body[1]
+                off = 8 if ver == 1 else 4
+                shape = tuple(struct.unpack_from("<Q", body, off + 8 * i)[0] for i in range(rank))
+            elif mtype == 0x3:
+                cls, bits0 = body[0] & 0x0F, body[1]
+                sz = struct.unpack_from("<I", body, 4)[0]
+                if cls == 1 and not (bits0 & 1) and sz in (4, 8):
+                    dtype = np.dtype("<f%d" % sz)
+            elif mtype == 0x8 and body[0] == 3 and body[1] == 1:
+                addr, size = struct.unpack_from("<Q", body, 2)[0], struct.unpack_from("<Q", body, 10)[0]
+        if shape is None or dtype is None or addr is None or addr == 0xFFFFFFFFFFFFFFFF:
+            return None
+        return self.base + addr, size, shape, dtype
+
     def dataset(self, entry):
         """-> numpy array, or None when the object is not a contiguous little-endian float dataset"""
         shape = dtype = None
@@ -265,3 +284,55 @@ def keras_h5_to_blob(path):
             raise H5Error("%s/%s has shape %s, expected %s" % (layer, pname, arr.shape, shape))
         blob[off:off + arr.size] = arr.astype(np.float32).reshape(-1)
     return blob
+
+
+def blob_to_keras_h5(blob, template_path, out_path):
+    """Writes ``blob`` as a Keras ``.h5`` model file the reference's ``load_model`` reads (training_pipeline.py:186-191,
+    345, 515-516) WITHOUT h5py / TensorFlow: ``template_path`` is any model file the reference itself saved for this
+    architecture (``data/model/Checkers_Model*.h5``); its HDF5 structure, ``model_config`` and training configuration
+    are kept byte for byte and only the payloads of the weight datasets (contiguous, uncompressed float32) are replaced.
+    The optimizer state that Keras stored next to the weights is zeroed (a fresh Adam).  -> out_path"""
+    blob = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
+    if blob.size != _N.NET_PARAM_COUNT:
+        raise H5Error("weight blob has %d values, expected %d" % (blob.size, _N.NET_PARAM_COUNT))
+    with open(template_path, "rb") as f:
+        data = bytearray(f.read())
+    h5 = _File(bytes(data))
+    extents = {}
+
+    def walk(entry, name):
+        kids = h5.children(entry)
+        if kids:
+            for k, e in kids:
+                walk(e, name + "/" + k if name else k)
+        else:
+            ext = h5.dataset_extent(entry)
+            if ext is not None:
+                extents[name] = ext
+
+    for k, e in h5.children(h5.root):
+        walk(e, k)
+    roles = layer_roles(model_config(bytes(data)))
+    by_layer = {}
+    for name, ext in extents.items():
+        parts = name.split("/")
+        if parts[0] == "model_weights" and len(parts) >= 3:
+            by_layer.setdefault(parts[1], {})[parts[-1].split(":")[0]] = ext
+        elif parts[0] == "optimizer_weights":
+            off, size, _shape, _dt = ext
+            data[off:off + size] = bytes(size)                           # Adam moments of the template's training run
+    bn_names = {"bn_gamma": "gamma", "bn_beta": "beta", "bn_mean": "moving_mean", "bn_var": "moving_variance"}
+    for key, (boff, shape) in _N.layout().items():
+        role, param = key.split("/")
+        layer, pname = (roles[role + "/bn"], bn_names[param]) if param in bn_names else (roles[role], param)
+        try:
+            off, size, fshape, dt = by_layer[layer][pname]
+        except KeyError:
+            raise H5Error("template has no dataset %s/%s (for %s)" % (layer, pname, key))
+        n = int(np.prod(shape))
+        if tuple(fshape) != tuple(shape) or size != n * dt.itemsize:
+            raise H5Error("template dataset %s/%s has shape %s, expected %s" % (layer, pname, fshape, shape))
+        data[off:off + size] = blob[boff:boff + n].astype(dt).tobytes()
+    with open(out_path, "wb") as f:
+        f.write(data)
+    return out_path

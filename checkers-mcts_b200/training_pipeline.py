@@ -84,11 +84,19 @@ def set_nn_lrate(neural_network, lrate):
     neural_network.base_lr = lrate
 
 
-def save_nn_to_disk(neural_network, iteration, timestamp):
-    """Save the network with timestamp and iteration in the file name (reference :186-191); the weights are
-    written as a .npy blob, which every NN_FN consumer of this package accepts."""
+def save_nn_to_disk(neural_network, iteration, timestamp, h5_template=None):
+    """Save the network with timestamp and iteration in the file name (reference :186-191).  The weights are written as
+    a .npy blob, which every NN_FN consumer of this package accepts.  With ``h5_template`` (or the environment variable
+    CK_H5_TEMPLATE) naming any model file the reference saved (data/model/Checkers_Model*.h5), a Keras ``.h5`` the
+    reference's own ``load_model`` reads is written next to it (``ckb200.h5lite.blob_to_keras_h5``: the template's HDF5
+    structure with the weight payloads replaced; no h5py / TensorFlow needed)."""
     filename = 'data/model/Checkers_Model' + str(iteration) + '_' + timestamp + '.npy'
-    return neural_network.save(filename)
+    out = neural_network.save(filename)
+    h5_template = h5_template or os.environ.get('CK_H5_TEMPLATE')
+    if h5_template:
+        from ckb200 import h5lite
+        h5lite.blob_to_keras_h5(neural_network.blob(), h5_template, filename[:-4] + '.h5')
+    return out
 
 
 def plot_history(history, nn, TRAINING_ITERATION):

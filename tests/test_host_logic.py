@@ -284,3 +284,39 @@ def test_packed_records_round_trip():
         raise AssertionError("truncated word stream accepted")
     except ValueError:
         pass
+
+
+def test_keras_h5_export_through_a_reference_template(tmp_path):
+    """weights written back as a Keras .h5 (reference training_pipeline.py:186-191 saves .h5): the HDF5 structure,
+    model_config and training configuration of a file the reference itself saved are kept byte for byte, the weight
+    payloads are replaced, the stored optimizer state is zeroed.  Read back with the importer, blob for blob."""
+    import pytest
+    d = "/root/reference/data/model"
+    if not os.path.isdir(d):
+        pytest.skip("reference models not mounted")
+    from ckb200 import h5lite
+    fns = sorted(f for f in os.listdir(d) if f.endswith(".h5"))
+    template = os.path.join(d, [f for f in fns if "Model5_" in f][0])
+    other = h5lite.keras_h5_to_blob(os.path.join(d, [f for f in fns if "Model10_" in f][0]))
+    blob = (other * np.float32(1.25) + np.float32(0.001)).astype(np.float32)       # weights that are in no shipped file
+    out = h5lite.blob_to_keras_h5(blob, template, str(tmp_path / "Checkers_Model11_test.h5"))
+    assert os.path.getsize(out) == os.path.getsize(template)
+    assert h5lite.keras_h5_to_blob(out).tobytes() == blob.tobytes()
+    a, b = open(template, "rb").read(), open(out, "rb").read()
+    assert h5lite.model_config(a) == h5lite.model_config(b)
+    # nothing but dataset payloads changed: the bytes that differ lie inside float datasets
+    da, _ = h5lite.read_datasets(out, prefix="optimizer_weights")
+    assert da and all((v == 0).all() for v in da.values())
+    diff = np.flatnonzero(np.frombuffer(a, np.uint8) != np.frombuffer(b, np.uint8))
+    assert 0 < len(diff) <= 3 * 4 * N.NET_PARAM_COUNT
+    # save_nn_to_disk writes it next to the .npy when a template is named
+    import training_pipeline as TP
+    from ckb200 import train as T
+    os.makedirs(tmp_path / "data" / "model")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        fn = TP.save_nn_to_disk(T.CheckersNet(blob), 12, "01-Jan-2026(00:00:00)", h5_template=template)
+        assert fn.endswith(".npy") and h5lite.keras_h5_to_blob(fn[:-4] + ".h5").tobytes() == blob.tobytes()
+    finally:
+        os.chdir(cwd)
