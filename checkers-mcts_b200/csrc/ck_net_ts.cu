@@ -60,6 +60,9 @@ __host__ __device__ constexpr int cf_slots(int ksteps) { return ksteps + (ksteps
 constexpr int kGcf = cf_slots(kKSteps0) + 7 * cf_slots(kKStepsL) + cf_slots(kKSteps8);   // 14 + 7 * 108 + 12 = 782 slot images
 constexpr int kNS = 16;                             // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
+#ifndef CK_TS_ARRIVE_EACH
+#define CK_TS_ARRIVE_EACH 0
+#endif
 #ifndef CK_TS_LOADER_SETS
 #define CK_TS_LOADER_SETS 2
 #endif
@@ -173,6 +176,24 @@ tower_ts_kernel(const TowerParams prm) {
                     r[j][4 * u] = v.x; r[j][4 * u + 1] = v.y; r[j][4 * u + 2] = v.z; r[j][4 * u + 3] = v.w;
                 }
             }
+#if CK_TS_ARRIVE_EACH
+            // every slot is announced as soon as its own store has landed: a stored slot that waits for the rest of its
+            // batch is ring capacity the MMA issuers cannot use (up to 3 of the 16 slots)
+#pragma unroll
+            for (int j = 0; j < kLoadGroup; ++j) {
+                const uint32_t ss = base + j;
+                if (ss < total) {
+                    const uint32_t slot = ss % kNS;
+                    mbar_wait(bar_empty(slot), ((ss / kNS) & 1u) ^ 1u);
+                    tc_fence_after();
+                    tmem_st16(t_w + slot * 16, r[j]);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full(slot));
+                }
+            }
+#else
 #pragma unroll
             for (int j = 0; j < kLoadGroup; ++j) {
                 const uint32_t ss = base + j;
@@ -191,6 +212,7 @@ tower_ts_kernel(const TowerParams prm) {
                 for (int j = 0; j < kLoadGroup; ++j)
                     if (base + j < total) mbar_arrive(bar_full((base + j) % kNS));
             }
+#endif
         }
     } else if (warp >= kMmaWarp0) {
         // ===== MMA issuers, one warp per tile.  The whole warp runs the loop converged; elect.sync
