@@ -437,9 +437,9 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": gpu_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (split-fp16 tensor-core passes, fp32 accumulate)" if args.net_impl == "tc" else "f32",
             "data": "synthetic", "config": workload_config(world)}
-    line["config"]["net_impl"] = args.net_impl
-    line["config"]["eval_cache"] = "off" if args.no_eval_cache else "on (per-slot, 16384 entries)"
-    line["config"]["steady_state"] = ("warm start: the first game of slot i plays its first hash(i) mod %d plies at %d sims/move and everything "
+    # how this arm ran the workload (kept out of `config`, which is the workload both arms share)
+    line["engine"] = {"net_impl": args.net_impl, "eval_cache": "off" if args.no_eval_cache else "on (per-slot, 16384 entries)"}
+    line["engine"]["steady_state"] = ("warm start: the first game of slot i plays its first hash(i) mod %d plies at %d sims/move and everything "
                                       "after that at %d, so slots reach full-budget play at scattered game stages; untimed pre-roll of %d rounds "
                                       "(%d moves, %d games ended), then %d warm-up steps" %
                                       (PREROLL_PLIES, PREROLL_BUDGET, BUDGET, pre["rounds"], pre["moves"], pre["games"], args.warmup))
