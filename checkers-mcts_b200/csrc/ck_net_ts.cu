@@ -58,8 +58,15 @@ constexpr int kG = kKSteps0 + 7 * kKStepsL + kKSteps8;   // 521 k-steps = the wh
 // consecutive k-steps [phase B: 2 main MMAs], so every slot still feeds exactly two MMAs per tile.
 __host__ __device__ constexpr int cf_slots(int ksteps) { return ksteps + (ksteps + 1) / 2; }
 constexpr int kGcf = cf_slots(kKSteps0) + 7 * cf_slots(kKStepsL) + cf_slots(kKSteps8);   // 14 + 7 * 108 + 12 = 782 slot images
-constexpr int kNS = 16;                             // TMEM weight ring slots (16 columns each)
+#ifndef CK_TS_RING_LOG2
+#define CK_TS_RING_LOG2 4
+#endif
+constexpr int kNSLog2 = CK_TS_RING_LOG2;            // (3 = an 8-slot ring: the experiment that shows how much the ring's depth matters)
+constexpr int kNS = 1 << kNSLog2;                   // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
+#ifndef CK_TS_ISSUE2
+#define CK_TS_ISSUE2 1
+#endif
 #ifndef CK_TS_ARRIVE_EACH
 #define CK_TS_ARRIVE_EACH 0
 #endif
@@ -241,10 +248,30 @@ tower_ts_kernel(const TowerParams prm) {
                     // phase A: the cross terms of every k-step of the layer (slot = Whi | Wlo of one k-step)
                     for (int tap = tap_lo; tap < tap_hi; ++tap) {
                         uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
+#if CK_TS_ISSUE2
+                        if (nk == 8) {
+                            // two slots per trip of the issuing loop (the per-slot overhead of waiting, fencing and electing
+                            // is what the 1.5x more slots of this order cost)
+#pragma unroll 1
+                            for (int kc = 0; kc < 8; kc += 2, s += 2) {
+                                const uint32_t s0 = s & (kNS - 1), s1 = (s + 1) & (kNS - 1);
+                                mbar_wait(bar_full(s0), (s >> kNSLog2) & 1u);
+                                mbar_wait(bar_full(s1), ((s + 1) >> kNSLog2) & 1u);
+                                tc_fence_after();
+                                const uint64_t bh0 = kDescHi | (uint64_t)(kDescLo + b), bh1 = bh0 + (uint64_t)((2 * kChunkStride) >> 4);
+                                tc_quad_ts_elect(d, kWCol0 + s0 * 16, bh0 + (uint64_t)(kSplitBytes >> 4), kWCol0 + s0 * 16 + 8, bh0,
+                                                 kWCol0 + s1 * 16, bh1 + (uint64_t)(kSplitBytes >> 4), kWCol0 + s1 * 16 + 8, bh1, kIdesc, acc,
+                                                 bar_empty(s0), bar_empty(s1));
+                                acc = 1u;
+                                b += (uint32_t)(4 * kChunkStride) >> 4;
+                            }
+                            continue;
+                        }
+#endif
 #pragma unroll 1
                         for (int kc = 0; kc < nk; ++kc, ++s) {
                             const uint32_t slot = s & (kNS - 1);
-                            mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                            mbar_wait(bar_full(slot), (s >> kNSLog2) & 1u);
                             tc_fence_after();
                             const uint64_t bhi = kDescHi | (uint64_t)(kDescLo + b);
                             tc_pair_ts_elect(d, kWCol0 + slot * 16, bhi + (uint64_t)(kSplitBytes >> 4),      // Whi * Alo
@@ -259,7 +286,7 @@ tower_ts_kernel(const TowerParams prm) {
 #pragma unroll 1
                         for (int j = 0; j < 5; ++j, ++s) {
                             const uint32_t slot = s & (kNS - 1);
-                            mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                            mbar_wait(bar_full(slot), (s >> kNSLog2) & 1u);
                             tc_fence_after();
                             const int t0 = 2 * j, t1 = 2 * j + 1 < 9 ? 2 * j + 1 : 2 * j;
                             const uint32_t b0 = tile16 + (uint32_t)(kP * (t0 / 3) * 10 + t0 % 3), b1 = tile16 + (uint32_t)(kP * (t1 / 3) * 10 + t1 % 3);
@@ -269,16 +296,30 @@ tower_ts_kernel(const TowerParams prm) {
                     } else {
                         for (int tap = tap_lo; tap < tap_hi; ++tap) {
                             uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
+#if CK_TS_ISSUE2
+#pragma unroll 1
+                            for (int kc = 0; kc < 8; kc += 4, s += 2) {
+                                const uint32_t s0 = s & (kNS - 1), s1 = (s + 1) & (kNS - 1);
+                                mbar_wait(bar_full(s0), (s >> kNSLog2) & 1u);
+                                mbar_wait(bar_full(s1), ((s + 1) >> kNSLog2) & 1u);
+                                tc_fence_after();
+                                const uint64_t b0 = kDescHi | (uint64_t)(kDescLo + b), st = (uint64_t)((2 * kChunkStride) >> 4);
+                                tc_quad_ts_elect(d, kWCol0 + s0 * 16, b0, kWCol0 + s0 * 16 + 8, b0 + st, kWCol0 + s1 * 16, b0 + 2 * st,
+                                                 kWCol0 + s1 * 16 + 8, b0 + 3 * st, kIdesc, 1u, bar_empty(s0), bar_empty(s1));
+                                b += (uint32_t)(8 * kChunkStride) >> 4;
+                            }
+#else
 #pragma unroll 1
                             for (int kc = 0; kc < 8; kc += 2, ++s) {
                                 const uint32_t slot = s & (kNS - 1);
-                                mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                                mbar_wait(bar_full(slot), (s >> kNSLog2) & 1u);
                                 tc_fence_after();
                                 const uint64_t b0 = kDescHi | (uint64_t)(kDescLo + b);
                                 tc_pair_ts_elect(d, kWCol0 + slot * 16, b0, kWCol0 + slot * 16 + 8, b0 + (uint64_t)((2 * kChunkStride) >> 4),
                                                  kIdesc, 1u, bar_empty(slot));
                                 b += (uint32_t)(4 * kChunkStride) >> 4;
                             }
+#endif
                         }
                     }
                 } else
@@ -287,7 +328,7 @@ tower_ts_kernel(const TowerParams prm) {
 #pragma unroll 1
                     for (int kc = 0; kc < nk; ++kc, ++s) {
                         const uint32_t slot = s & (kNS - 1);
-                        mbar_wait(bar_full(slot), (s >> 4) & 1u);
+                        mbar_wait(bar_full(slot), (s >> kNSLog2) & 1u);
                         tc_fence_after();
                         tc_kstep_ts_elect(d, kWCol0 + slot * 16, kDescHi | (uint64_t)(kDescLo + b), (uint32_t)(kSplitBytes >> 4), kIdesc, acc,
                                           bar_empty(slot));            // 2 arrivals (X and Y) free the slot

@@ -106,6 +106,25 @@ __device__ __forceinline__ void tc_pair_ts_elect(uint32_t d_tmem, uint32_t a0, u
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
         "}\n" ::"r"(d_tmem), "r"(a0), "l"(b0), "r"(a1), "l"(b1), "r"(idesc), "r"(accumulate), "r"(bar) : "memory");
 }
+// Two weight slots in one go: four MMAs, each slot's commit right after its pair
+__device__ __forceinline__ void tc_quad_ts_elect(uint32_t d_tmem, uint32_t a0, uint64_t b0, uint32_t a1, uint64_t b1,
+                                                 uint32_t a2, uint64_t b2, uint32_t a3, uint64_t b3, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t bar_a, uint32_t bar_b) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e, t;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %10, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %9, p;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], %4, %9, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%5], %6, %9, t;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%7], %8, %9, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        "}\n" ::"r"(d_tmem), "r"(a0), "l"(b0), "r"(a1), "l"(b1), "r"(a2), "l"(b2), "r"(a3), "l"(b3), "r"(idesc), "r"(accumulate),
+        "r"(bar_a), "r"(bar_b) : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
     asm volatile(
         "{\n"
