@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "ckb200", "libckb200.so")
+OUT = os.environ.get("CK_BUILD_OUT") or os.path.join(HERE, "ckb200", "libckb200.so")   # CK_BUILD_OUT: experimental builds next to the product
 SOURCES = ["ck_movegen.cu", "ck_net.cu", "ck_net_tc.cu", "ck_net_ts.cu", "ck_heads_tc.cu", "ck_engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -34,7 +34,7 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not os.environ.get("CK_BUILD_OUT") else "build_exp")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("CK_NVCC_DEFS", "").split()   # tuning experiments: -DNAME=value
     objs = []

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libckb200.so")
+LIB_PATH = os.environ.get("CKB200_LIB") or os.path.join(_HERE, "libckb200.so")     # CKB200_LIB: an experimental build for A/B runs
 
 MAX_CHILDREN = 48
 POLICY_SIZE = 512

@@ -65,7 +65,7 @@ constexpr int kNSLog2 = CK_TS_RING_LOG2;            // (3 = an 8-slot ring: the 
 constexpr int kNS = 1 << kNSLog2;                   // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
 #ifndef CK_TS_ISSUE2
-#define CK_TS_ISSUE2 1
+#define CK_TS_ISSUE2 4
 #endif
 #ifndef CK_TS_ARRIVE_EACH
 #define CK_TS_ARRIVE_EACH 0
@@ -248,7 +248,30 @@ tower_ts_kernel(const TowerParams prm) {
                     // phase A: the cross terms of every k-step of the layer (slot = Whi | Wlo of one k-step)
                     for (int tap = tap_lo; tap < tap_hi; ++tap) {
                         uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
-#if CK_TS_ISSUE2
+#if CK_TS_ISSUE2 == 4
+                        if (nk == 8) {
+                            // four slots per trip of the issuing loop
+#pragma unroll 1
+                            for (int kc = 0; kc < 8; kc += 4, s += 4) {
+                                uint32_t aa[8], bars[4];
+                                uint64_t bb[8];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t sl = (s + i) & (kNS - 1);
+                                    mbar_wait(bar_full(sl), ((s + i) >> kNSLog2) & 1u);
+                                    const uint64_t bh = kDescHi | (uint64_t)(kDescLo + b + (uint32_t)((2 * i * kChunkStride) >> 4));
+                                    aa[2 * i] = kWCol0 + sl * 16; bb[2 * i] = bh + (uint64_t)(kSplitBytes >> 4);
+                                    aa[2 * i + 1] = kWCol0 + sl * 16 + 8; bb[2 * i + 1] = bh;
+                                    bars[i] = bar_empty(sl);
+                                }
+                                tc_fence_after();
+                                tc_oct_ts_elect(d, aa, bb, kIdesc, acc, bars);
+                                acc = 1u;
+                                b += (uint32_t)(8 * kChunkStride) >> 4;
+                            }
+                            continue;
+                        }
+#elif CK_TS_ISSUE2
                         if (nk == 8) {
                             // two slots per trip of the issuing loop (the per-slot overhead of waiting, fencing and electing
                             // is what the 1.5x more slots of this order cost)
@@ -296,7 +319,25 @@ tower_ts_kernel(const TowerParams prm) {
                     } else {
                         for (int tap = tap_lo; tap < tap_hi; ++tap) {
                             uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
-#if CK_TS_ISSUE2
+#if CK_TS_ISSUE2 == 4
+                            {
+                                uint32_t aa[8], bars[4];
+                                uint64_t bb[8];
+                                const uint64_t st = (uint64_t)((2 * kChunkStride) >> 4);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t sl = (s + i) & (kNS - 1);
+                                    mbar_wait(bar_full(sl), ((s + i) >> kNSLog2) & 1u);
+                                    const uint64_t b0 = kDescHi | (uint64_t)(kDescLo + b);
+                                    aa[2 * i] = kWCol0 + sl * 16; bb[2 * i] = b0 + (uint64_t)(2 * i) * st;
+                                    aa[2 * i + 1] = kWCol0 + sl * 16 + 8; bb[2 * i + 1] = b0 + (uint64_t)(2 * i + 1) * st;
+                                    bars[i] = bar_empty(sl);
+                                }
+                                tc_fence_after();
+                                tc_oct_ts_elect(d, aa, bb, kIdesc, 1u, bars);
+                                s += 4;
+                            }
+#elif CK_TS_ISSUE2
 #pragma unroll 1
                             for (int kc = 0; kc < 8; kc += 4, s += 2) {
                                 const uint32_t s0 = s & (kNS - 1), s1 = (s + 1) & (kNS - 1);

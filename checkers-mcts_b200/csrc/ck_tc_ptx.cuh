@@ -125,6 +125,31 @@ __device__ __forceinline__ void tc_quad_ts_elect(uint32_t d_tmem, uint32_t a0, u
         "}\n" ::"r"(d_tmem), "r"(a0), "l"(b0), "r"(a1), "l"(b1), "r"(a2), "l"(b2), "r"(a3), "l"(b3), "r"(idesc), "r"(accumulate),
         "r"(bar_a), "r"(bar_b) : "memory");
 }
+// Four weight slots in one go (a[2i], a[2i+1] / b[2i], b[2i+1]: the two MMAs of slot i; bar[i]: its commit)
+__device__ __forceinline__ void tc_oct_ts_elect(uint32_t d_tmem, const uint32_t a[8], const uint64_t b[8], uint32_t idesc,
+                                                uint32_t accumulate, const uint32_t bar[4]) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e, t;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %18, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %9, %17, p;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %10, %17, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%19];\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%3], %11, %17, t;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%4], %12, %17, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%20];\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%5], %13, %17, t;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%6], %14, %17, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%21];\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%7], %15, %17, t;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%8], %16, %17, t;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%22];\n"
+        "}\n" ::"r"(d_tmem), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "l"(b[0]), "l"(b[1]), "l"(b[2]), "l"(b[3]), "l"(b[4]), "l"(b[5]), "l"(b[6]), "l"(b[7]), "r"(idesc), "r"(accumulate),
+        "r"(bar[0]), "r"(bar[1]), "r"(bar[2]), "r"(bar[3]) : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
     asm volatile(
         "{\n"
