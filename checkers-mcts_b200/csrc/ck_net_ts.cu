@@ -64,6 +64,9 @@ constexpr int kGcf = cf_slots(kKSteps0) + 7 * cf_slots(kKStepsL) + cf_slots(kKSt
 constexpr int kNSLog2 = CK_TS_RING_LOG2;            // (3 = an 8-slot ring: the experiment that shows how much the ring's depth matters)
 constexpr int kNS = 1 << kNSLog2;                   // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
+#ifndef CK_TS_FAKE_EPI
+#define CK_TS_FAKE_EPI 0
+#endif
 #ifndef CK_TS_ISSUE2
 #define CK_TS_ISSUE2 4
 #endif
@@ -456,6 +459,9 @@ tower_ts_kernel(const TowerParams prm) {
                 const float *bias_p = prm.blob + prm.bias_off[layer];
                 const uint32_t st_base = smem_u32(smem) + (uint32_t)(t * kTileBytes) + ((lane >> 4) ? (uint32_t)kSplitBytes : 0u) +
                                          (uint32_t)((4 * quad + ((lane >> 3) & 1)) * kChunkStride + sq_off(0, 1, (lane & 7) + 1));
+#if CK_TS_FAKE_EPI == 2
+                mbar_arrive(bar_act_ready(t));                  // TIMING EXPERIMENT ONLY: the next layer starts at once, the epilogue work still runs
+#endif
                 __half2 amax = __float2half2_rn(0.f);           // range guard: largest |hi half| this thread wrote
                 float vp[16];                                   // value conv1x1 partial sums (conv6 epilogue only)
 #pragma unroll
@@ -470,6 +476,9 @@ tower_ts_kernel(const TowerParams prm) {
                     float wv0 = 0.f, wv1 = 0.f;
                     if (layer == 6) { wv0 = prm.blob[prm.val1x1_k + ch0]; wv1 = prm.blob[prm.val1x1_k + ch0 + 8]; }
                     tmem_ld_wait32(cur);
+#if CK_TS_FAKE_EPI == 1
+                    if (prm.max_n > 0) continue;          // TIMING EXPERIMENT ONLY: how much of the launch is exposed epilogue work
+#endif
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int g = 8 * sub + j;
@@ -530,7 +539,9 @@ tower_ts_kernel(const TowerParams prm) {
                 }
                 fence_proxy_async();
                 tc_fence_before();
+#if CK_TS_FAKE_EPI != 2
                 mbar_arrive(bar_act_ready(t));
+#endif
                 if (t) el1 = layer + 1; else el0 = layer + 1;
             } else {
                 // fused policy conv1x1 128 -> 8 (+ bias, ReLU, BN; training_pipeline.py:89-96): accumulator rows 0..7,
