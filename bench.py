@@ -355,10 +355,12 @@ def run_ours(args, rank, world, local_rank):
     if args.preroll > 0:
         st = eng.run(args.preroll)
         pre = dict(rounds=int(st["steps"]), games=int(st["games_finished"]), moves=int(st["moves"]))
-        eng.records_new(rec_buf)                  # the pre-roll's records are not the bench's
+        while eng.records_new(rec_buf)[1] > 0:    # the pre-roll's records are not the bench's (drained in buffer-sized pieces)
+            pass
     for _ in range(args.warmup):
         eng.run(args.rounds)
-        eng.records_new(rec_buf)
+        while eng.records_new(rec_buf)[1] > 0:
+            pass
     eng.set_profile(True)
     sampler = ClockSampler(dev)
     if rank == 0:
