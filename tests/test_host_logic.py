@@ -320,3 +320,27 @@ def test_keras_h5_export_through_a_reference_template(tmp_path):
         assert fn.endswith(".npy") and h5lite.keras_h5_to_blob(fn[:-4] + ".h5").tobytes() == blob.tobytes()
     finally:
         os.chdir(cwd)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (CPU only): the reference's own self-play code timed on the host cores prints the
+    contract's JSON line -- same metric / unit / config as the CUDA arm, `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    import sys
+    from oracle import build_ref
+    from oracle import ref_harness as H
+    if not (H.reference_available() or build_ref.available()):
+        import pytest
+        pytest.skip("neither the reference tree nor its compiled copy (oracle/_ref) is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mcts_sims_per_sec" and d["unit"] == "sims/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "4096 concurrent self-play games" in d["config"]["workload"] and d["gpu_launches"] == 0
