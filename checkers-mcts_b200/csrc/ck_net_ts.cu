@@ -64,6 +64,13 @@ constexpr int kGcf = cf_slots(kKSteps0) + 7 * cf_slots(kKStepsL) + cf_slots(kKSt
 constexpr int kNSLog2 = CK_TS_RING_LOG2;            // (3 = an 8-slot ring: the experiment that shows how much the ring's depth matters)
 constexpr int kNS = 1 << kNSLog2;                   // TMEM weight ring slots (16 columns each)
 constexpr int kWCol0 = 256;                         // first weight column; accumulators: X [0,128), Y [128,256)
+// A layer's epilogue writes its output channels in two time halves (TMEM lanes 0-15 of every quadrant, then 16-31), i.e.
+// first the input channels of the next layer's even k-steps, then those of its odd ones.  With CK_TS_HALF_SPLIT the next
+// layer's cross-term MMAs of the even k-steps start after the first half (act_ready_a) and only the odd ones wait for the
+// second (act_ready_b): half of an otherwise exposed epilogue hides behind 36 weight slots of tensor work.
+#ifndef CK_TS_HALF_SPLIT
+#define CK_TS_HALF_SPLIT 1
+#endif
 #ifndef CK_TS_FAKE_EPI
 #define CK_TS_FAKE_EPI 0
 #endif
@@ -142,14 +149,17 @@ tower_ts_kernel(const TowerParams prm) {
     auto bar_full = [&](uint32_t s) { return bar0 + 8u * s; };
     auto bar_empty = [&](uint32_t s) { return bar0 + 8u * (kNS + s); };
     auto bar_acc_full = [&](int t) { return bar0 + 8u * (2 * kNS + t); };
-    auto bar_act_ready = [&](int t) { return bar0 + 8u * (2 * kNS + 2 + t); };
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kBarOff + 8 * (2 * kNS + 4));
+    auto bar_act_ready = [&](int t) { return bar0 + 8u * (2 * kNS + 2 + t); };        // first half of the channels (all of them for layer 0's input)
+    auto bar_act_ready_b = [&](int t) { return bar0 + 8u * (2 * kNS + 4 + t); };      // second half
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kBarOff + 8 * (2 * kNS + 6));
 
     for (int i = tid * 16; i < 2 * kTileBytes; i += (int)blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
     if (warp == kMmaWarp0) {
         if (lane == 0) {
             for (int s = 0; s < kNS; ++s) { mbar_init(bar_full(s), 4); mbar_init(bar_empty(s), (uint32_t)prm.tiles); }
-            for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 32 * kEpiWarps); }
+            for (int t = 0; t < 2; ++t) {
+                mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 32 * kEpiWarps); mbar_init(bar_act_ready_b(t), 32 * kEpiWarps);
+            }
             mbar_init_fence();
             reinterpret_cast<int *>(smem + kVredOff + 2 * 4 * kN * 4)[0] = 0;
             reinterpret_cast<int *>(smem + kVredOff + 2 * 4 * kN * 4)[1] = 0;
@@ -242,7 +252,10 @@ tower_ts_kernel(const TowerParams prm) {
         for (uint32_t pair = 0; pair < npu; ++pair) {
             if (pair >= np) break;
             for (int layer = 0; layer < kLayers; ++layer) {
-                mbar_wait(bar_act_ready(t), ar_phase); ar_phase ^= 1u;
+                constexpr bool kSplit = kCrossFirst && CK_TS_HALF_SPLIT && CK_TS_ISSUE2 == 4;
+                mbar_wait(bar_act_ready(t), ar_phase);
+                if (!kSplit || layer == 0) mbar_wait(bar_act_ready_b(t), ar_phase);     // (both halves flip together, one phase bit serves)
+                ar_phase ^= 1u;
                 tc_fence_after();
                 const int nk = layer == 0 ? 1 : 8;
                 const int tap_lo = layer == kLayers - 1 ? 4 : 0, tap_hi = layer == kLayers - 1 ? 5 : 9;   // conv1x1 = centre tap
@@ -253,6 +266,7 @@ tower_ts_kernel(const TowerParams prm) {
                         uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3);
 #if CK_TS_ISSUE2 == 4
                         if (nk == 8) {
+                            if (kSplit) break;                // handled below: even k-steps of every tap, then the odd ones
                             // four slots per trip of the issuing loop
 #pragma unroll 1
                             for (int kc = 0; kc < 8; kc += 4, s += 4) {
@@ -306,6 +320,33 @@ tower_ts_kernel(const TowerParams prm) {
                             b += (uint32_t)(2 * kChunkStride) >> 4;
                         }
                     }
+#if CK_TS_ISSUE2 == 4
+                    if (kSplit && nk == 8) {
+#pragma unroll 1
+                        for (int half = 0; half < 2; ++half) {
+                            if (half == 1) { mbar_wait(bar_act_ready_b(t), ar_phase ^ 1u); tc_fence_after(); }   // the phase bit was flipped above
+#pragma unroll 1
+                            for (int tap = tap_lo; tap < tap_hi; ++tap, s += 4) {
+                                // k-steps half, half + 2, half + 4, half + 6 of this tap: 16 input channels each, two 8-channel chunks apart
+                                const uint32_t b = tile16 + (uint32_t)(kP * (tap / 3) * 10 + tap % 3) + (uint32_t)((2 * half * kChunkStride) >> 4);
+                                uint32_t aa[8], bars[4];
+                                uint64_t bb[8];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t sl = (s + i) & (kNS - 1);
+                                    mbar_wait(bar_full(sl), ((s + i) >> kNSLog2) & 1u);
+                                    const uint64_t bh = kDescHi | (uint64_t)(kDescLo + b + (uint32_t)((4 * i * kChunkStride) >> 4));
+                                    aa[2 * i] = kWCol0 + sl * 16; bb[2 * i] = bh + (uint64_t)(kSplitBytes >> 4);
+                                    aa[2 * i + 1] = kWCol0 + sl * 16 + 8; bb[2 * i + 1] = bh;
+                                    bars[i] = bar_empty(sl);
+                                }
+                                tc_fence_after();
+                                tc_oct_ts_elect(d, aa, bb, kIdesc, acc, bars);
+                                acc = 1u;
+                            }
+                        }
+                    }
+#endif
                     // phase B: Whi * Ahi, two consecutive k-steps per slot
                     if (layer == 0) {
                         // nine k-steps (one per tap, 16 input channels): pairs of taps, the tenth half-slot holds zeros
@@ -428,6 +469,7 @@ tower_ts_kernel(const TowerParams prm) {
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar_act_ready(t));
+            mbar_arrive(bar_act_ready_b(t));
         };
 
         build_input(0, 0);
@@ -459,9 +501,6 @@ tower_ts_kernel(const TowerParams prm) {
                 const float *bias_p = prm.blob + prm.bias_off[layer];
                 const uint32_t st_base = smem_u32(smem) + (uint32_t)(t * kTileBytes) + ((lane >> 4) ? (uint32_t)kSplitBytes : 0u) +
                                          (uint32_t)((4 * quad + ((lane >> 3) & 1)) * kChunkStride + sq_off(0, 1, (lane & 7) + 1));
-#if CK_TS_FAKE_EPI == 2
-                mbar_arrive(bar_act_ready(t));                  // TIMING EXPERIMENT ONLY: the next layer starts at once, the epilogue work still runs
-#endif
                 __half2 amax = __float2half2_rn(0.f);           // range guard: largest |hi half| this thread wrote
                 float vp[16];                                   // value conv1x1 partial sums (conv6 epilogue only)
 #pragma unroll
@@ -476,6 +515,13 @@ tower_ts_kernel(const TowerParams prm) {
                     float wv0 = 0.f, wv1 = 0.f;
                     if (layer == 6) { wv0 = prm.blob[prm.val1x1_k + ch0]; wv1 = prm.blob[prm.val1x1_k + ch0 + 8]; }
                     tmem_ld_wait32(cur);
+                    if (h == 1) {
+                        // the accumulator is read out completely and the first half of the channels (TMEM lanes 0-15 of every
+                        // quadrant = the next layer's even k-steps) is in shared memory: the next layer may start on those
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(bar_act_ready(t));
+                    }
 #if CK_TS_FAKE_EPI == 1
                     if (prm.max_n > 0) continue;          // TIMING EXPERIMENT ONLY: how much of the launch is exposed epilogue work
 #endif
@@ -539,9 +585,7 @@ tower_ts_kernel(const TowerParams prm) {
                 }
                 fence_proxy_async();
                 tc_fence_before();
-#if CK_TS_FAKE_EPI != 2
-                mbar_arrive(bar_act_ready(t));
-#endif
+                mbar_arrive(bar_act_ready_b(t));
                 if (t) el1 = layer + 1; else el0 = layer + 1;
             } else {
                 // fused policy conv1x1 128 -> 8 (+ bias, ReLU, BN; training_pipeline.py:89-96): accumulator rows 0..7,
@@ -635,7 +679,16 @@ __global__ void wpack_cf_kernel(const float *__restrict__ blob, PackAux aux, con
         while (g >= cf_slots(ksteps)) { g -= cf_slots(ksteps); ++layer; ksteps = layer < kTowerConvs ? kKStepsL : kKSteps8; }
         int kstep;
         bool lo;
-        if (g < ksteps) { kstep = g; lo = (u & 2) != 0; }                       // phase A: hi | lo of one k-step
+        if (g < ksteps) {                                                       // phase A: hi | lo of one k-step
+            kstep = g;
+#if CK_TS_HALF_SPLIT && CK_TS_ISSUE2 == 4
+            // the even k-steps (input channels 0-15, 32-47, ...) of every tap first, then the odd ones: the order in which the
+            // previous layer's epilogue delivers the channels
+            if (ksteps == kKStepsL) { const int half = g / 36, r = g % 36; kstep = (r >> 2) * 8 + 2 * (r & 3) + half; }
+            else if (ksteps == kKSteps8 && layer == kTowerConvs) { kstep = 2 * (g & 3) + (g >> 2); }
+#endif
+            lo = (u & 2) != 0;
+        }
         else { kstep = 2 * (g - ksteps) + ((u & 2) ? 1 : 0); lo = false; }      // phase B: hi of two k-steps
         int tap, ci0;
         if (layer == 0) { tap = kstep; ci0 = 0; }
