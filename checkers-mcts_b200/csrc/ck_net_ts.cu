@@ -33,6 +33,7 @@
 // 16 epilogue warps, splitting act_ready so the next layer starts on the first half of the channels.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "ck_net.cuh"
 #include "ck_tc_ptx.cuh"
 
@@ -505,6 +506,9 @@ tower_ts_kernel(const TowerParams prm) {
                 float vp[16];                                   // value conv1x1 partial sums (conv6 epilogue only)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) vp[i] = 0.f;
+                // one code copy per "does this layer's output also feed the value head" (conv6): the test is out of the inner loop
+                auto epilogue_halves = [&](auto val_tag) {
+                constexpr bool kVal = decltype(val_tag)::value;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     tmem_ld_16x256b_x8_async(((uint32_t)(quad * 32 + 16 * h) << 16) + (uint32_t)(t * kN + 64 * sub), cur);
@@ -513,7 +517,7 @@ tower_ts_kernel(const TowerParams prm) {
                     const float sc0 = fold[ch0] * kActScale, sc1 = fold[ch0 + 8] * kActScale;
                     const float sh0 = fold[kC + ch0] * kActScale, sh1 = fold[kC + ch0 + 8] * kActScale;
                     float wv0 = 0.f, wv1 = 0.f;
-                    if (layer == 6) { wv0 = prm.blob[prm.val1x1_k + ch0]; wv1 = prm.blob[prm.val1x1_k + ch0 + 8]; }
+                    if (kVal) { wv0 = prm.blob[prm.val1x1_k + ch0]; wv1 = prm.blob[prm.val1x1_k + ch0 + 8]; }
                     tmem_ld_wait32(cur);
                     if (h == 1) {
                         // the accumulator is read out completely and the first half of the channels (TMEM lanes 0-15 of every
@@ -532,7 +536,7 @@ tower_ts_kernel(const TowerParams prm) {
                         const float a1 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 1]), inv, bias0), 0.f), sc0, sh0);
                         const float a2 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 2]), inv, bias1), 0.f), sc1, sh1);
                         const float a3 = fmaf(fmaxf(fmaf(__uint_as_float(cur[4 * j + 3]), inv, bias1), 0.f), sc1, sh1);
-                        if (layer == 6) {
+                        if (kVal) {
                             vp[2 * j] = fmaf(wv1, a2, fmaf(wv0, a0, vp[2 * j]));
                             vp[2 * j + 1] = fmaf(wv1, a3, fmaf(wv0, a1, vp[2 * j + 1]));
                         }
@@ -545,6 +549,8 @@ tower_ts_kernel(const TowerParams prm) {
                                           *reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
                     }
                 }
+                };
+                if (layer == 6) epilogue_halves(std::true_type{}); else epilogue_halves(std::false_type{});
                 if (layer == 6) {
                     // value head conv1x1 128 -> 1 (training_pipeline.py:102-105) on the conv6 output while it is in
                     // registers: reduce over the 8 lanes that hold different channels, park the per-quadrant
