@@ -130,6 +130,11 @@ class MCTS(object):
         """BUDGET new simulations from ``root_node`` on top of any inherited statistics
         (MCTS.py:210-224)."""
         start = datetime.now()
+        if cls.multiproc and not cls.neural_net:
+            # MCTS.py:83-87 hands pool.map's (outcome, player) tuples to backpropagation, and the first simulation ends in
+            # this TypeError (observed with the unmodified reference); the batched playout evaluator is the parallel path here
+            raise TypeError("unsupported operand type(s) for +=: 'int' and 'tuple' (MULTIPROC=True with NEURAL_NET=False "
+                            "fails like this in the reference; playouts already run in parallel on the device, pass MULTIPROC=False)")
         net = getattr(cls.game_env, 'neural_net', None)
         tree = root_node._tree
         if tree is not None and not tree.closed and tree.kind == "net" and tree.net is not net \

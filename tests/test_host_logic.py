@@ -254,6 +254,23 @@ def test_play_checkers_move_listing_and_record_q():
     assert R.to_reference(rec)[2] == np.float32(7.0) / np.float32(150.0)
 
 
+def test_multiproc_playouts_fail_like_the_reference():
+    """MULTIPROC=True with NEURAL_NET=False: the reference's first simulation raises a TypeError (MCTS.py:83-87 feeds
+    pool.map's tuples to backpropagation; observed with the unmodified reference), the shim raises the same before
+    it touches the device"""
+    import pytest
+    import MCTS as M
+    kw = dict(GAME_ENV=None, UCT_C=4, CONSTRAINT='rollout', BUDGET=4, MULTIPROC=True, NEURAL_NET=False, VERBOSE=False,
+              TRAINING=False, DIRICHLET_ALPHA=1.0, DIRICHLET_EPSILON=0.25, TEMPERATURE_TAU=0, TEMPERATURE_DECAY=0,
+              TEMP_DECAY_DELAY=0)
+    M.MCTS(**kw)
+    try:
+        with pytest.raises(TypeError, match="'int' and 'tuple'"):
+            M.MCTS.begin_tree_search(object())
+    finally:
+        M.MCTS(**dict(kw, MULTIPROC=False))
+
+
 def test_packed_records_round_trip():
     """ckb200.records.pack / unpack (numpy twins of the device-side pack kernel and of what rank 0 does after the
     gather): bit-identical round trip on real game records, including a terminal record that carries its legal-action
