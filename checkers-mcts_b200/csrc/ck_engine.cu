@@ -976,7 +976,8 @@ __global__ void round_begin_kernel(const EngineDev E) {
             if (E.wave > 0) {
                 // a leaf that waits costs its slot a whole evaluate-then-chain cycle (~2.4 simulations at cfg2), a wave iteration
                 // saved is worth ~590 of them: cutting the batch back pays while the excess is below ~0.5 wave (measured
-                // break-even, profiles/r2e_steady_sweep.jsonl); applied below 0.3 wave
+                // break-even, profiles/r2e_steady_sweep.jsonl); applied below 0.4 wave (the long-run cfg2 state asks for
+                // 6.25-6.33 waves every round, profiles/r2y_batch_hist.jsonl; 0.3 -> 0.4: +4 %, profiles/r2z_slack.jsonl)
                 const int asked = c->batch_count[k] + c->deferred[k];       // previous round of this group
                 const int full = asked / E.wave * E.wave;
                 if (full >= E.wave && (asked - full) * 10 < E.wave_slack10 * E.wave) cap = full;
@@ -1245,7 +1246,8 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
         // CK_BATCH_WAVES=0 switches it off; CK_BATCH_WAVES=n (> 1) forces a wave of n rows for every evaluator (tests)
         static const int shape_env = getenv("CK_BATCH_WAVES") ? atoi(getenv("CK_BATCH_WAVES")) : -1;
         const int wave = 4 * num_sms(cfg->device);
-        d.wave_slack10 = shape_env > 1 ? 10 : 3;                 // forced mode always cuts back (every round defers leaves)
+        static const int slack_env = getenv("CK_BATCH_SLACK10") ? atoi(getenv("CK_BATCH_SLACK10")) : -1;   // measurement knob
+        d.wave_slack10 = shape_env > 1 ? 10 : (slack_env >= 0 ? slack_env : 4);     // forced mode always cuts back (every round defers leaves)
         if (shape_env > 1) d.wave = cfg->arena ? 0 : shape_env;
         else d.wave = (shape_env != 0 && cfg->evaluator == CK_EVAL_NET && !cfg->arena && cfg->n_slots >= 2 * wave) ? wave : 0;
     }
