@@ -337,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
     base, stride, _n = D.shard(args.slots * world, rank, world)          # game g -> rank g mod world
     cfg = L.make_cfg(n_slots=args.slots, budget=BUDGET, device=dev, evaluator="net", keep_records=True,
                      seed=20261017, game_id_base=base, game_id_stride=stride,
-                     eval_cache_entries=-1 if args.no_eval_cache else 0,
+                     eval_cache_entries=-1 if args.no_eval_cache else args.cache_entries, max_chain_per_step=args.max_chain,
                      stagger_budget=PREROLL_BUDGET if args.preroll > 0 else 0, stagger_plies=PREROLL_PLIES if args.preroll > 0 else 0, **MCTS)
     eng = L.Engine(cfg)
     eng.set_net(0, net)
@@ -440,7 +440,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f32 (split-fp16 tensor-core passes, fp32 accumulate)" if args.net_impl == "tc" else "f32",
             "data": "synthetic", "config": workload_config(world)}
     # how this arm ran the workload (kept out of `config`, which is the workload both arms share)
-    line["engine"] = {"net_impl": args.net_impl, "eval_cache": "off" if args.no_eval_cache else "on (per-slot, 16384 entries)"}
+    line["engine"] = {"net_impl": args.net_impl, "eval_cache": "off" if args.no_eval_cache else "on (per-slot, %s entries, chain cap %s)" % (args.cache_entries or "default", args.max_chain or "default")}
     line["engine"]["steady_state"] = ("warm start: the first game of slot i plays its first hash(i) mod %d plies at %d sims/move and everything "
                                       "after that at %d, so slots reach full-budget play at scattered game stages; untimed pre-roll of %d rounds "
                                       "(%d moves, %d games ended), then %d warm-up steps" %
@@ -556,6 +556,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the generate_data() wall-clock measurement")
     ap.add_argument("--no-eval-cache", action="store_true", help="evaluate every leaf (A/B of the evaluation cache)")
+    ap.add_argument("--cache-entries", type=int, default=0, help="evaluation cache entries per slot (0: the engine's default)")
+    ap.add_argument("--max-chain", type=int, default=0, help="simulations a slot may chain inside one round (0: the engine's default)")
     ap.add_argument("--preroll", type=int, default=PREROLL_ROUNDS)
     ap.add_argument("--pipeline-games", type=int, default=SLOTS)
     ap.add_argument("--pipeline-workers", type=int, default=32, help="NUM_CPUS of the generate_data() call (files written)")

@@ -1221,7 +1221,7 @@ ck_engine *ck_engine_create(const ck_engine_cfg *cfg) {
     // per round the steady-state tree_step took 0.35 ms instead of 0.1 ms: scripts/long_run.py), so the
     // default lets a slot finish four and carries the rest into the next rounds.
     d.max_term = cfg->max_terminal_sims_per_step > 0 ? cfg->max_terminal_sims_per_step : 4;
-    d.max_chain = cfg->max_chain_per_step > 0 ? cfg->max_chain_per_step : 8;
+    d.max_chain = cfg->max_chain_per_step > 0 ? cfg->max_chain_per_step : 6;      // 4 / 5 / 6 / 7 / 8 / 10 measured, profiles/r3c, r3d
     if (d.max_chain < d.max_term) d.max_chain = d.max_term;
     // evaluation cache: per slot a power of two of 128-byte entries (default 16384 = 2 MB per slot, 8.6 GB at cfg2: hit
     // rate 41.8 % / 44.1 % at 4096 / 16384 entries in the warm-started bench, +4 % simulations/s); the playout modes
