@@ -8,7 +8,7 @@ Workload (BASELINE.json configs[1]): 4096 concurrent self-play games per GPU, 40
 Dirichlet(alpha=1, eps=0.25) at every node, tau=1 with decay, TERMINATE_CNT=200, random-init network (seed 0); slots
 are refilled when their game ends.  One "step" = 400 lock-step rounds (tree kernel + batched network evaluation).
 
-Steady state: the slots are desynchronised by a warm start (the first game of slot i plays its first hash(i) mod 140 plies
+Steady state: the slots are desynchronised by a warm start (the first game a slot plays (game g) plays its first hash(g) mod 140 plies
 at 8 sims/move, everything after that at 400) and an untimed pre-roll of about one game length at full budget, so the
 timed region sees games at every stage with trees and evaluation caches as deep as in a long run, finishing games
 included, instead of 4096 openings in lock step.  Then 2K steps alternate:
@@ -42,7 +42,7 @@ SLOTS = 4096
 BUDGET = 400
 ROUNDS_PER_STEP = 400
 PREROLL_BUDGET = 8            # sims/move of the opening plies a slot's first game plays before full-budget play (warm start)
-PREROLL_PLIES = 140           # slot i does that for hash(i) mod 140 plies: stages spread over a typical game length
+PREROLL_PLIES = 140           # game g does that for hash(g) mod 140 plies: stages spread over a typical game length
 PREROLL_ROUNDS = 24000        # untimed rounds (~28 s): about one game length at full budget, so trees and evaluation caches are as deep as in a long run
 REF_PLIES = 2                 # plies per game of a reference-arm sample (the reference's TERMINATE_CNT knob)
 TOWER_FLOP_PER_POS = 2 * (9 * 14 * 128 * 64 + 7 * 9 * 128 * 128 * 64 + 128 * 8 * 64)   # 134,316,032: the eight 3x3 convs + the policy conv1x1 the tower kernel evaluates
@@ -441,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic", "config": workload_config(world)}
     # how this arm ran the workload (kept out of `config`, which is the workload both arms share)
     line["engine"] = {"net_impl": args.net_impl, "eval_cache": "off" if args.no_eval_cache else "on (per-slot, %s entries, chain cap %s)" % (args.cache_entries or "default", args.max_chain or "default")}
-    line["engine"]["steady_state"] = ("warm start: the first game of slot i plays its first hash(i) mod %d plies at %d sims/move and everything "
+    line["engine"]["steady_state"] = ("warm start: the first game a slot plays (game g) plays its first hash(g) mod %d plies at %d sims/move and everything "
                                       "after that at %d, so slots reach full-budget play at scattered game stages; untimed pre-roll of %d rounds "
                                       "(%d moves, %d games ended), then %d warm-up steps" %
                                       (PREROLL_PLIES, PREROLL_BUDGET, BUDGET, pre["rounds"], pre["moves"], pre["games"], args.warmup))

@@ -718,10 +718,11 @@ __device__ void init_game(const WarpCtx &c, int local_game) {
         S.buf[0] = 0; S.buf[1] = 1; S.scratch = 2;
         S.exists[0] = S.exists[1] = 0;
         S.nrec = 0; S.misses = 0; S.search_id = 0; S.g_sims0 = S.tot_sims; S.g_evals0 = S.tot_evals;
-        // warm start (benchmarks): the first game of a slot plays a slot-specific number of opening plies at a small budget,
-        // so that the slots reach full-budget play at different stages of their games instead of in lock step
+        // warm start (benchmarks): the first game of a slot plays a number of opening plies at a small budget, so that the
+        // slots reach full-budget play at different stages of their games instead of in lock step.  The number is a
+        // function of the GAME (which slot claims which game depends on warp scheduling; records must not)
         S.stagger_until = (c.E.cfg.stagger_plies > 0 && S.tot_sims == 0)
-                              ? (int32_t)(mix32((uint32_t)c.slot * 0x9E3779B1u ^ (uint32_t)c.E.cfg.seed) % (uint32_t)c.E.cfg.stagger_plies) : 0;
+                              ? (int32_t)(mix32((uint32_t)local_game * 0x9E3779B1u ^ (uint32_t)c.E.cfg.seed) % (uint32_t)c.E.cfg.stagger_plies) : 0;
         if (!c.E.cfg.reference_tau_quirk || S.tau < -1e300) S.tau = c.E.cfg.tau;
         c.hist[0] = start_position();
     }

@@ -162,8 +162,8 @@ typedef struct {
                                  * before in the same slot is expanded from the cached priors / value: same numbers, no network call */
     int32_t max_chain_per_step; /* simulations a slot may complete inside one round without a network evaluation
                                  * (terminal children + cache hits); 0: default 6 */
-    int32_t stagger_budget;   /* warm start for throughput measurements: the FIRST game of slot i plays its first */
-    int32_t stagger_plies;    /* hash(i) mod stagger_plies plies at stagger_budget sims/move, every later move (and game) at
+    int32_t stagger_budget;   /* warm start for throughput measurements: the first game a slot plays (staged game g) plays its first */
+    int32_t stagger_plies;    /* hash(g) mod stagger_plies plies at stagger_budget sims/move, every later move (and game) at
                                * BUDGET, so the slots reach full-budget play at scattered stages of their games.  0: off */
     int32_t reserved0;
 } ck_engine_cfg;

@@ -442,6 +442,42 @@ def test_batch_shaping_is_transparent():
     assert k == len(a[0])
 
 
+def test_production_size_batch_shaping_is_transparent():
+    """the shaping rule as it runs in production: 4096 slots, the network evaluator, the default 4 x SMs wave and 0.4-wave
+    cut-back threshold (at cfg2 it caps every round of the steady state).  The records of 4096 warm-started games must be
+    the same bytes with the rule switched off (CK_BATCH_WAVES=0) and with a different chain cap, and the shaped run must
+    really have deferred leaves (it needs more rounds for the same games)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, json, hashlib; sys.path[:0] = %r\n"
+        "import numpy as np\n"
+        "from ckb200 import lib, net as N\n"
+        "net = lib.Net(0); net.set_weights(N.random_init_blob(3))\n"
+        "eng = lib.Engine(lib.make_cfg(n_slots=4096, budget=96, training=True, terminate_cnt=24, evaluator='net', seed=5,\n"
+        "                              stagger_budget=8, stagger_plies=16, max_chain_per_step=int(sys.argv[1])))\n"
+        "eng.set_net(0, net)\n"
+        "st = eng.selfplay(4096)\n"
+        "r = eng.records(); r = r[np.lexsort((r['ply'], r['game']))]\n"
+        "print(json.dumps(dict(steps=st['steps'], sims=st['sims'], evals=st['nn_evals'] - st['cache_hits'], records=len(r),\n"
+        "                      sha=hashlib.sha256(r.tobytes()).hexdigest())))\n") % ([ROOT, PKG],)
+    outs = {}
+    for name, waves, chain in (("off", "0", 0), ("default", None, 0), ("chain2", None, 2)):
+        env = dict(os.environ)
+        env.pop("CK_BATCH_WAVES", None)
+        env.pop("CK_BATCH_SLACK10", None)
+        if waves is not None:
+            env["CK_BATCH_WAVES"] = waves
+        r = subprocess.run([sys.executable, "-c", code, str(chain)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    off, dflt, chain2 = outs["off"], outs["default"], outs["chain2"]
+    assert off["records"] == dflt["records"] == chain2["records"] and off["records"] >= 4096 * 8
+    assert off["sha"] == dflt["sha"] == chain2["sha"], outs
+    assert off["sims"] == dflt["sims"] == chain2["sims"]
+    assert dflt["steps"] > off["steps"], outs            # leaves were deferred: more rounds, each with fewer tower iterations
+
+
 def test_overlapped_groups_are_transparent():
     """CK_OVERLAP=1: the slots form two groups and the tree kernel of one runs on a second stream next to the tower of the
     other (one-warp blocks, per-group batches and counters).  Same records, bit for bit, as the single-stream engine
