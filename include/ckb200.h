@@ -152,7 +152,9 @@ typedef struct {
     int32_t evaluator_p2;     /* arena with stub evaluators: evaluator of the second net; -1: same */
     int32_t arena;            /* 0 self-play (one net); 1 arena: net 0 is player1 in games < n/2 (:523-528) */
     int32_t keep_records;     /* store training records (self-play) */
-    int32_t reference_tau_quirk; /* 1: tau is never reset between games */
+    int32_t reference_tau_quirk; /* 1: tau is never reset between games: a game inherits the tau its SLOT's
+                                  * previous game ended with (0 once a game has outlasted the decay, so every later game is arg-max
+                                  * play as in the reference); which slot claims a later game is not fixed when several end in one round */
     int32_t game_id_base;     /* global id of local game i = base + i*stride (multi-GPU sharding) */
     int32_t game_id_stride;   /* 0 is treated as 1 */
     int32_t max_terminal_sims_per_step; /* simulations ending in a terminal child that a slot may finish inside one round; 0: default 4 */
