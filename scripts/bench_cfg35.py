@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--sims3", type=int, default=800)
     ap.add_argument("--games5", type=int, default=1024)
     ap.add_argument("--skip", default="")
+    ap.add_argument("--chain", type=int, default=0, help="max_chain_per_step of both engines (0: the engine's default)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -57,7 +58,7 @@ def main():
         base, stride, n_local = D.shard(args.games3, rank, world)
         eng = L.Engine(L.make_cfg(n_slots=n_local, budget=args.sims3, device=local, training=True, terminate_cnt=200, evaluator="net",
                                   keep_records=True, uct_c=4.0, alpha=1.0, epsilon=0.25, tau=1.0, tau_decay=0.1, tau_decay_delay=10,
-                                  seed=3, game_id_base=base, game_id_stride=stride))
+                                  seed=3, game_id_base=base, game_id_stride=stride, max_chain_per_step=args.chain))
         eng.set_net(0, nets[0])
         if world > 1:
             dist.barrier()
@@ -89,7 +90,7 @@ def main():
         base, stride, n_local = D.shard(args.games5, rank, world)
         eng = L.Engine(L.make_cfg(n_slots=n_local, budget=400, device=local, training=False, terminate_cnt=0, evaluator="net", arena=True,
                                   keep_records=False, uct_c=4.0, alpha=1.0, epsilon=0.25, tau=0.0, seed=5, max_plies=1024,
-                                  game_id_base=base, game_id_stride=stride))
+                                  game_id_base=base, game_id_stride=stride, max_chain_per_step=args.chain))
         eng.set_net(0, nets[0])
         eng.set_net(1, nets[1])
         if world > 1:
