@@ -101,7 +101,7 @@ def gather_engine_records(engine, rank, world, device, dst=0, want_info=False, u
     RECORD_DTYPE, ``ms`` their sum, ``bytes`` on the wire.  ``unpack=False`` returns (headers, words) instead of decoding."""
     import time
     import torch
-    from . import records as R
+    from . import lib as L
     from .lib_types import RECORD_HDR_DTYPE
     dev = torch.device(device)
     torch.cuda.synchronize(dev)
@@ -125,7 +125,7 @@ def gather_engine_records(engine, rank, world, device, dst=0, want_info=False, u
         nbytes = H.numel() + 4 * W.numel()
         hdr = H.cpu().numpy().view(RECORD_HDR_DTYPE)
         words = W.cpu().numpy().view(np.uint32)
-        out = R.unpack(hdr, words) if unpack else (hdr, words)
+        out = L.records_unpack(hdr, words) if unpack else (hdr, words)      # host-side C twin of records.unpack
     t2 = time.time()
     info = dict(ms=1000.0 * (t2 - t0), gather_ms=1000.0 * (t1 - t0), decode_ms=1000.0 * (t2 - t1), bytes=nbytes)
     return (out, info) if want_info else (out, info["ms"])

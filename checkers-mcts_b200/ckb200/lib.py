@@ -102,6 +102,7 @@ def _load():
     L.ck_records_fetch_new.argtypes = [vp, vp, i64, vp, vp]
     L.ck_records_pack_device.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     L.ck_records_fetch_packed.argtypes = [vp, vp, i64, vp, i64, vp, vp]
+    L.ck_records_unpack.argtypes = [vp, i64, vp, i64, vp]
     L.ck_engine_set_profile.argtypes = [vp, C.c_int]
     L.ck_engine_set_budget.argtypes = [vp, i32]
     L.ck_tree_set_root.argtypes = [vp, vp, i32]
@@ -272,6 +273,19 @@ class Net(object):
 
 
 # ---- engine --------------------------------------------------------------------------------
+def records_unpack(hdr, words):
+    """packed records (RECORD_HDR_DTYPE array, uint32 child words) -> RECORD_DTYPE array; host-side C twin of
+    ckb200.records.unpack (no device needed), multi-threaded"""
+    hdr = np.ascontiguousarray(hdr, dtype=RECORD_HDR_DTYPE)
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    out = np.empty(len(hdr), dtype=RECORD_DTYPE)
+    rc = _lib.ck_records_unpack(_ptr(hdr) if len(hdr) else None, len(hdr), _ptr(words) if len(words) else None, len(words),
+                                _ptr(out) if len(out) else None)
+    if rc != 0:
+        raise ValueError(_lib.ck_last_error().decode())
+    return out
+
+
 def make_cfg(n_slots, budget, device=0, uct_c=4.0, training=False, alpha=1.0, epsilon=0.0, tau=0.0,
              tau_decay=0.0, tau_decay_delay=0, terminate_cnt=0, seed=1, evaluator="net", evaluator_p2=None,
              arena=False, keep_records=True, pool_cap=0, max_plies=0, reference_tau_quirk=False,

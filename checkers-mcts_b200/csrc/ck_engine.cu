@@ -23,6 +23,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 #include "ck_common.cuh"
 #include "ck_device_fn.cuh"
@@ -1760,6 +1761,48 @@ int ck_records_fetch_packed(ck_engine *e, ck_record_hdr *hdr, int64_t hdr_cap, u
     cudaFree(d_hdr); cudaFree(d_words);
     if (ce != cudaSuccess) return fail(CK_ERR_CUDA, std::string("ck_records_fetch_packed: ") + cudaGetErrorString(ce));
     return rc;
+}
+
+// Packed records -> ck_record structs on the host (no device work): the inverse of the pack kernels, for consumers of
+// ck_records_fetch_packed / the pooled gather that want the full structs.  The legal-action planes are rebuilt from the
+// children's action ids (plane = a >> 6, square of (x, y) = ((a >> 3) & 7, a & 7) is 4x + (y >> 1)).
+int ck_records_unpack(const ck_record_hdr *hdr, int64_t n, const uint32_t *words, int64_t n_words, ck_record *out) {
+    if (n < 0 || n_words < 0 || (n > 0 && (!hdr || !out)) || (n_words > 0 && !words))
+        return fail(CK_ERR_ARG, "ck_records_unpack: bad arguments");
+    std::vector<int64_t> offs((size_t)n + 1);
+    offs[0] = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int nch = hdr[i].n_children;
+        if (nch > CK_MAX_CHILDREN) return fail(CK_ERR_ARG, "ck_records_unpack: a header claims more than CK_MAX_CHILDREN children");
+        offs[i + 1] = offs[i] + nch + (((hdr[i].flags & 1u) && nch == 0) ? 8 : 0);
+    }
+    if (offs[n] != n_words)
+        return fail(CK_ERR_ARG, "packed records: " + std::to_string((long long)offs[n]) + " child words expected, " +
+                                std::to_string((long long)n_words) + " present");
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const ck_record_hdr &h = hdr[i];
+            ck_record &r = out[i];
+            memset(&r, 0, sizeof(r));
+            r.pos = h.pos; r.q = h.q; r.root_w = h.root_w; r.root_n = h.root_n; r.game = h.game;
+            r.ply = h.ply; r.chosen = h.chosen; r.n_children = h.n_children; r.plane5 = h.plane5; r.z = h.z;
+            const uint32_t *w = words + offs[i];
+            for (int c = 0; c < (int)h.n_children; ++c) {
+                const uint32_t a = w[c] >> 23;
+                r.action[c] = (uint16_t)a;
+                r.visits[c] = w[c] & 0x7FFFFFu;
+                r.mask[a >> 6] |= 1u << (4u * ((a >> 3) & 7u) + ((a & 7u) >> 1));
+            }
+            if ((h.flags & 1u) && h.n_children == 0) memcpy(r.mask, w, 8 * sizeof(uint32_t));
+        }
+    };
+    const int64_t per = 1 << 16;
+    int nt = (int)std::min<int64_t>((n + per - 1) / per, std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u));
+    if (nt <= 1) { work(0, n); return CK_OK; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto &th : pool) th.join();
+    return CK_OK;
 }
 
 // ---- single-search API (slot 0) -----------------------------------------------------------

@@ -273,7 +273,7 @@ class generate_Checkers_data(object):
                 if world > 1:                             # packed on the device, exact-size NCCL transfers to rank 0
                     recs, _ms = _D.gather_engine_records(eng, rank, world, "cuda:%d" % device)
                 else:
-                    recs = _R.unpack(*eng.records_packed())     # a fifth of the bytes of the full records over PCIe
+                    recs = _L.records_unpack(*eng.records_packed())     # a fifth of the bytes of the full records over PCIe
             finally:                                      # device memory goes back also when a run fails
                 eng.close()
                 if net is not None:

@@ -256,6 +256,9 @@ int ck_records_pack_device(ck_engine *, ck_record_hdr *d_hdr, int64_t hdr_cap, u
                            int64_t *n_records, int64_t *n_words);
 int ck_records_fetch_packed(ck_engine *, ck_record_hdr *hdr, int64_t hdr_cap, uint32_t *words, int64_t word_cap,
                             int64_t *n_records, int64_t *n_words);
+/* packed records -> ck_record structs, on the host (no engine, no device): what a consumer of ck_records_fetch_packed or of
+ * the pooled gather (ckb200/dist.py) calls when it wants the full structs; fails if the child words do not add up */
+int ck_records_unpack(const ck_record_hdr *hdr, int64_t n_records, const uint32_t *words, int64_t n_words, ck_record *out);
 /* time the evaluator separately inside ck_engine_run (adds two events per step) */
 int ck_engine_set_profile(ck_engine *, int on);
 

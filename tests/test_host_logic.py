@@ -301,6 +301,20 @@ def test_packed_records_round_trip():
         raise AssertionError("truncated word stream accepted")
     except ValueError:
         pass
+    # the library's host-side unpack (ck_records_unpack, what generate_data() and the pooled gather call): same bytes,
+    # same error; also on a batch large enough for its worker threads, and on nothing at all
+    from ckb200 import lib as L
+    assert L.records_unpack(hdr, words).tobytes() == recs.tobytes()
+    big = np.concatenate([recs] * 2500)                             # > 2 x 65536 records
+    bh, bw = R.pack(big)
+    assert L.records_unpack(bh, bw).tobytes() == big.tobytes()
+    assert len(L.records_unpack(hdr[:0], words[:0])) == 0
+    for bad in (words[:-1], np.concatenate([words, words[:1]])):
+        try:
+            L.records_unpack(hdr, bad)
+            raise AssertionError("wrong word count accepted")
+        except ValueError as e:
+            assert "child words expected" in str(e)
 
 
 def test_keras_h5_export_through_a_reference_template(tmp_path):
